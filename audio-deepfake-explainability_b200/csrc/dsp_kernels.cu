@@ -1,0 +1,583 @@
+// DSP stage of the perturbation hot path on sm_100a (n_fft = 2048, hop = 512, periodic Hann):
+//   * stft_kernel ........... librosa-style centred STFT (zero padding) -> complex64 [frame][bin]       (once per track)
+//   * istft_masked_kernel ... per perturbed copy: mask generated on the fly in the load stage (occlusion rectangle or
+//                             per-bin band gain), inverse real FFT, synthesis window, overlap-add kept in REGISTERS while a
+//                             warp walks a strip of consecutive frames, window-sum-square normalisation, coalesced stores
+//   * mel_db_kernel ......... classifier front-end: reflect-padded STFT -> power -> HTK mel (sparse triangular filters)
+//                             -> 10 log10 -> [copy][frame][mel] + per-CTA maxima (for the top_db clamp)
+//   * mel_stats_kernel ...... clamp + sum / sum-of-squares partials (deterministic two-level reduction, fp64)
+//   * mel_resize_kernel ..... normalise ((x-mean)/(std+eps)), bilinear resize along time, bf16, written in both operand
+//                             layouts of the tokenizer GEMMs ([time][freq] and [freq][time])
+// All FFTs are warp-level (fft.cuh); HBM/L2 traffic is coalesced float2 / float4.
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "common.h"
+#include "fft.cuh"
+
+namespace b200x {
+
+constexpr int NFFT = 2048;
+constexpr int HOP = 512;
+constexpr int NBIN = 1025;
+constexpr int DSP_WARPS = 4;                    // warps per CTA for the FFT kernels
+constexpr int DSP_THREADS = DSP_WARPS * 32;
+constexpr int DSP_SMEM = DSP_WARPS * FFT_TILE * 8;
+
+__global__ void init_tables_kernel() {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2048) {
+        g_tw2048[i] = make_float2(static_cast<float>(cospi(i / 1024.0)), static_cast<float>(sinpi(i / 1024.0)));
+        g_hann[i] = static_cast<float>(0.5 - 0.5 * cospi(i / 1024.0));
+    }
+    if (i < 512) {
+        float acc = 0.f;
+        for (int j = 0; j < 4; ++j) {
+            const float w = static_cast<float>(0.5 - 0.5 * cospi((i + 512 * j) / 1024.0));
+            acc += w * w;
+        }
+        g_wss512[i] = acc;
+    }
+}
+
+static int ensure_tables(cudaStream_t stream) {
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [&] {
+        init_tables_kernel<<<8, 256, 0, stream>>>();
+        err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+    });
+    if (err != cudaSuccess) return set_error(B200X_ERR_CUDA, "table init failed: %s", cudaGetErrorString(err));
+    return B200X_OK;
+}
+
+// real 2048-sample frame packed as z[m] = x[2m] + i x[2m+1]; after the 1024-point FFT, X[k] for k = lane + 32 r
+// (and X[1024] on lane 0) is recovered from Z[k], Z[1024-k] staged in the warp tile.
+__device__ __forceinline__ void rfft_unpack(const float2 (&v)[32], float2* tile, int lane, float2 (&X)[32], float2& xnyq) {
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) tile[lane + 32 * r] = v[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const int k = lane + 32 * r;
+        const float2 zk = v[r];
+        const float2 zp = tile[(1024 - k) & 1023];
+        const float er = 0.5f * (zk.x + zp.x), ei = 0.5f * (zk.y - zp.y);
+        const float orr = 0.5f * (zk.y + zp.y), oi = -0.5f * (zk.x - zp.x);
+        const float2 w = __ldg(&g_tw2048[k]);                    // W = cos - i sin
+        X[r] = make_float2(er + orr * w.x + oi * w.y, ei - orr * w.y + oi * w.x);
+    }
+    const float2 z0 = tile[0];
+    xnyq = make_float2(z0.x - z0.y, 0.f);
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------ STFT (librosa)
+__global__ void __launch_bounds__(DSP_THREADS)
+stft_kernel(const float* __restrict__ y, long long n_samples, int n_frames, int reflect, float2* __restrict__ S,
+            int stride) {
+    extern __shared__ float2 dsp_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* tile = dsp_smem + warp * FFT_TILE;
+    for (int t = blockIdx.x * DSP_WARPS + warp; t < n_frames; t += gridDim.x * DSP_WARPS) {
+        const long long base = static_cast<long long>(t) * HOP - NFFT / 2;
+        float2 v[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int m = lane + 32 * r;
+            long long j0 = base + 2 * m, j1 = j0 + 1;
+            float a, b;
+            if (reflect) {
+                if (j0 < 0) j0 = -j0;
+                if (j1 < 0) j1 = -j1;
+                if (j0 >= n_samples) j0 = 2 * (n_samples - 1) - j0;
+                if (j1 >= n_samples) j1 = 2 * (n_samples - 1) - j1;
+                a = y[j0]; b = y[j1];
+            } else {
+                a = (j0 >= 0 && j0 < n_samples) ? y[j0] : 0.f;
+                b = (j1 >= 0 && j1 < n_samples) ? y[j1] : 0.f;
+            }
+            const float2 w = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
+            v[r] = make_float2(a * w.x, b * w.y);
+        }
+        fft1024_warp<false>(v, tile, lane);
+        float2 X[32], xn;
+        rfft_unpack(v, tile, lane, X, xn);
+        float2* row = S + static_cast<long long>(t) * stride;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) row[lane + 32 * r] = X[r];
+        if (lane == 0) row[1024] = xn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ masked iSTFT
+struct IstftParams {
+    const float2* S;          // [n_frames][stride]
+    int stride;
+    int n_frames;
+    long long out_len;        // samples written per copy = hop * (n_frames - 1)
+    long long out_stride;     // distance between copies in y
+    float* y;                 // [copies][out_stride]
+    const int* windows;       // mode 1: [copies][4] = t0, t1, f0, f1
+    float occlusion_value;
+    const float* gains;       // mode 2: [copies][NBIN]
+    int mode;                 // 0 none, 1 occlusion rectangle, 2 per-bin gain, 3 keep only the rectangle
+    int hops_per_strip;
+    double* sumsq;            // optional [copies]: sum of squares of the written samples (for RMS matching)
+};
+
+__global__ void __launch_bounds__(DSP_THREADS)
+istft_masked_kernel(IstftParams p) {
+    extern __shared__ float2 dsp_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* tile = dsp_smem + warp * FFT_TILE;
+    const int copy = blockIdx.y;
+    const int strip = blockIdx.x * DSP_WARPS + warp;
+    // padded hops [hp_a, hp_b) of this strip; valid output hops are 2 .. n_frames
+    const int hp_a = 2 + strip * p.hops_per_strip;
+    const int hp_b = min(hp_a + p.hops_per_strip, p.n_frames + 1);
+    if (hp_a >= hp_b) return;
+    int t0 = 0, t1 = 0, f0 = 0, f1 = 0;
+    if (p.mode == 1 || p.mode == 3) {
+        const int4 w = *reinterpret_cast<const int4*>(p.windows + 4 * copy);
+        t0 = w.x; t1 = w.y; f0 = w.z; f1 = w.w;
+    }
+    const float* gain = p.mode == 2 ? p.gains + static_cast<long long>(copy) * NBIN : nullptr;
+    float* yout = p.y + static_cast<long long>(copy) * p.out_stride;
+
+    float2 a0[8], a1[8], a2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = a2[i] = make_float2(0.f, 0.f);
+    float sq = 0.f;
+
+    for (int t = max(hp_a - 3, 0); t < hp_b; ++t) {
+        float2 v[32];
+        if (t < p.n_frames) {
+            const float2* row = p.S + static_cast<long long>(t) * p.stride;
+            const bool t_in = (t >= t0 && t < t1);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int k = lane + 32 * r, kp = 1024 - k;
+                float2 xk = __ldg(&row[k]);
+                float2 xp = __ldg(&row[kp]);
+                if (p.mode == 1) {
+                    if (t_in && k >= f0 && k < f1) xk = make_float2(p.occlusion_value, 0.f);
+                    if (t_in && kp >= f0 && kp < f1) xp = make_float2(p.occlusion_value, 0.f);
+                } else if (p.mode == 3) {
+                    if (!(t_in && k >= f0 && k < f1)) xk = make_float2(0.f, 0.f);
+                    if (!(t_in && kp >= f0 && kp < f1)) xp = make_float2(0.f, 0.f);
+                } else if (p.mode == 2) {
+                    const float gk = __ldg(&gain[k]), gp = __ldg(&gain[kp]);
+                    xk.x *= gk; xk.y *= gk; xp.x *= gp; xp.y *= gp;
+                }
+                if (k == 0) xk.y = 0.f;                 // irfft ignores the imaginary part of DC ...
+                if (kp == 1024) xp.y = 0.f;             // ... and of Nyquist
+                const float er = 0.5f * (xk.x + xp.x), ei = 0.5f * (xk.y - xp.y);
+                const float dr = 0.5f * (xk.x - xp.x), di = 0.5f * (xk.y + xp.y);
+                const float2 w = __ldg(&g_tw2048[k]);    // e^{+i theta} = (cos, +sin)
+                const float orr = dr * w.x - di * w.y, oi = dr * w.y + di * w.x;
+                v[r] = make_float2(er - oi, ei + orr);
+            }
+            fft1024_warp<true>(v, tile, lane);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const float2 w = *reinterpret_cast<const float2*>(&g_hann[2 * (lane + 32 * r)]);
+                v[r] = make_float2(v[r].x * w.x * (1.0f / 1024.0f), v[r].y * w.y * (1.0f / 1024.0f));
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = make_float2(0.f, 0.f);
+        }
+        // overlap-add: frame chunk q = r / 8 lands on padded hop t + q; hop t is now complete
+        if (t >= hp_a) {
+            const bool steady = (t >= 3 && t <= p.n_frames - 1);
+            const long long n_base = static_cast<long long>(t - 2) * HOP;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int slot = 2 * lane + 64 * i;
+                float2 o = make_float2(a0[i].x + v[i].x, a0[i].y + v[i].y);
+                float2 wss;
+                if (steady) {
+                    wss = *reinterpret_cast<const float2*>(&g_wss512[slot]);
+                } else {
+                    wss = make_float2(0.f, 0.f);
+                    for (int j = 0; j < 4; ++j) {
+                        const int tf = t - j;
+                        if (tf >= 0 && tf < p.n_frames) {
+                            const float2 w = *reinterpret_cast<const float2*>(&g_hann[j * HOP + slot]);
+                            wss.x += w.x * w.x; wss.y += w.y * w.y;
+                        }
+                    }
+                }
+                if (wss.x > 1.17549435e-38f) o.x /= wss.x;
+                if (wss.y > 1.17549435e-38f) o.y /= wss.y;
+                if (n_base + slot < p.out_len) {
+                    *reinterpret_cast<float2*>(yout + n_base + slot) = o;
+                    sq += o.x * o.x + o.y * o.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a0[i] = make_float2(a1[i].x + v[8 + i].x, a1[i].y + v[8 + i].y);
+            a1[i] = make_float2(a2[i].x + v[16 + i].x, a2[i].y + v[16 + i].y);
+            a2[i] = v[24 + i];
+        }
+    }
+    if (p.sumsq != nullptr) {
+        double d = static_cast<double>(sq);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) atomicAdd(p.sumsq + copy, d);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ mel front-end
+struct MelParams {
+    const float* y;            // [copies][y_stride]
+    long long y_stride;
+    long long n_samples;
+    const double* sumsq;       // optional RMS matching: per-copy sum of squares of y, and the reference RMS
+    double ref_rms;
+    long long rms_count;
+    int n_frames;
+    int n_mels;                // <= 128, multiple of 32
+    const int* fb_start;       // [n_mels] first bin with a non-zero weight
+    const int* fb_count;       // [n_mels]
+    const int* fb_offset;      // [n_mels] offset into fb_weights
+    const float* fb_weights;
+    float amin;
+    float* db;                 // [copies][n_frames][n_mels]
+    float* cta_max;            // [copies][gridDim.x]
+    int frames_per_cta;
+};
+
+__global__ void __launch_bounds__(DSP_THREADS)
+mel_db_kernel(MelParams p) {
+    extern __shared__ float2 dsp_smem[];
+    __shared__ float s_max[DSP_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* tile = dsp_smem + warp * FFT_TILE;
+    float* pw = reinterpret_cast<float*>(tile);
+    const int copy = blockIdx.y;
+    const float* y = p.y + static_cast<long long>(copy) * p.y_stride;
+    float gain = 1.0f;
+    if (p.sumsq != nullptr) {                         // match_rms (src/dsp_band_ops.py:228-233), float64 like the reference
+        const double r_x = sqrt(p.sumsq[copy] / static_cast<double>(p.rms_count) + 1e-8);
+        if (!(r_x < 1e-8)) gain = static_cast<float>(p.ref_rms / r_x);
+    }
+    float vmax = -INFINITY;
+    const int f_begin = blockIdx.x * p.frames_per_cta;
+    const int f_end = min(f_begin + p.frames_per_cta, p.n_frames);
+    for (int t = f_begin + warp; t < f_end; t += DSP_WARPS) {
+        const long long base = static_cast<long long>(t) * HOP - NFFT / 2;
+        float2 v[32];
+        const bool interior = (base >= 0) && (base + NFFT <= p.n_samples);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int m = lane + 32 * r;
+            float2 s;
+            if (interior) {
+                s = *reinterpret_cast<const float2*>(y + base + 2 * m);
+            } else {                                   // reflect padding (torch.stft center=True, pad_mode='reflect')
+                long long j0 = base + 2 * m, j1 = j0 + 1;
+                if (j0 < 0) j0 = -j0;
+                if (j1 < 0) j1 = -j1;
+                if (j0 >= p.n_samples) j0 = 2 * (p.n_samples - 1) - j0;
+                if (j1 >= p.n_samples) j1 = 2 * (p.n_samples - 1) - j1;
+                s = make_float2(y[j0], y[j1]);
+            }
+            const float2 w = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
+            v[r] = make_float2(s.x * gain * w.x, s.y * gain * w.y);
+        }
+        fft1024_warp<false>(v, tile, lane);
+        float2 X[32], xn;
+        rfft_unpack(v, tile, lane, X, xn);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) pw[lane + 32 * r] = X[r].x * X[r].x + X[r].y * X[r].y;
+        if (lane == 0) pw[1024] = xn.x * xn.x;
+        __syncwarp();
+        float* out = p.db + (static_cast<long long>(copy) * p.n_frames + t) * p.n_mels;
+        for (int f = lane; f < p.n_mels; f += 32) {
+            const int st = __ldg(&p.fb_start[f]), cnt = __ldg(&p.fb_count[f]);
+            const float* w = p.fb_weights + __ldg(&p.fb_offset[f]);
+            float acc = 0.f;
+            for (int i = 0; i < cnt; ++i) acc = fmaf(__ldg(&w[i]), pw[st + i], acc);
+            const float d = 10.0f * log10f(fmaxf(acc, p.amin));
+            out[f] = d;
+            vmax = fmaxf(vmax, d);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) s_max[warp] = vmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = s_max[0];
+        for (int i = 1; i < DSP_WARPS; ++i) m = fmaxf(m, s_max[i]);
+        p.cta_max[static_cast<long long>(copy) * gridDim.x + blockIdx.x] = m;
+    }
+}
+
+// clamp at (max - top_db) and reduce sum / sum of squares: partial[copy][block] = (sum, sumsq), fp64
+__global__ void __launch_bounds__(256)
+mel_stats_kernel(const float* __restrict__ db, long long per_copy, const float* __restrict__ cta_max, int n_cta_max,
+                 float top_db, double2* __restrict__ partial, float* __restrict__ floor_out) {
+    __shared__ float s_floor;
+    __shared__ double s_a[8], s_b[8];
+    const int copy = blockIdx.y;
+    if (threadIdx.x == 0) {
+        float m = -INFINITY;
+        for (int i = 0; i < n_cta_max; ++i) m = fmaxf(m, cta_max[static_cast<long long>(copy) * n_cta_max + i]);
+        s_floor = m - top_db;
+        if (blockIdx.x == 0) floor_out[copy] = s_floor;
+    }
+    __syncthreads();
+    const float fl = s_floor;
+    const float4* src = reinterpret_cast<const float4*>(db + static_cast<long long>(copy) * per_copy);
+    const long long n4 = per_copy / 4;
+    double a = 0.0, b = 0.0;
+    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 x = src[i];
+        const float v0 = fmaxf(x.x, fl), v1 = fmaxf(x.y, fl), v2 = fmaxf(x.z, fl), v3 = fmaxf(x.w, fl);
+        a += static_cast<double>(v0) + v1 + v2 + v3;
+        b += static_cast<double>(v0) * v0 + static_cast<double>(v1) * v1 + static_cast<double>(v2) * v2 +
+             static_cast<double>(v3) * v3;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int i = 0; i < 8; ++i) { sa += s_a[i]; sb += s_b[i]; }
+        partial[static_cast<long long>(copy) * gridDim.x + blockIdx.x] = make_double2(sa, sb);
+    }
+}
+
+// normalise + bilinear resize along time (F.interpolate(mode='bilinear', align_corners=False); the mel axis keeps its
+// size so its weights are exactly (1, 0)) -> bf16 in [time][mel] (temporal tokenizer operand) and [mel][time] (spectral)
+struct ResizeParams {
+    const float* db;           // [copies][n_frames][n_mels]
+    const double2* partial;
+    const float* floor_val;
+    int n_partial;
+    int n_frames, n_mels, out_t;
+    int unbiased;
+    float eps;
+    __nv_bfloat16* img_t;      // [copies][out_t][n_mels]
+    __nv_bfloat16* img_f;      // [copies][n_mels][ld_f]
+    int ld_f;
+};
+
+__global__ void __launch_bounds__(256)
+mel_resize_kernel(ResizeParams p) {
+    __shared__ float s_mean, s_inv;
+    __shared__ __nv_bfloat16 s_tile[64][128 + 2];
+    const int copy = blockIdx.y;
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int i = 0; i < p.n_partial; ++i) {
+            const double2 v = p.partial[static_cast<long long>(copy) * p.n_partial + i];
+            sa += v.x; sb += v.y;
+        }
+        const double n = static_cast<double>(p.n_frames) * p.n_mels;
+        const double mean = sa / n;
+        const double var = fmax((sb - n * mean * mean) / (p.unbiased ? n - 1.0 : n), 0.0);
+        s_mean = static_cast<float>(mean);
+        s_inv = 1.0f / (static_cast<float>(sqrt(var)) + p.eps);
+    }
+    __syncthreads();
+    const float mean = s_mean, inv = s_inv, fl = p.floor_val[copy];
+    const float scale = static_cast<float>(p.n_frames) / static_cast<float>(p.out_t);
+    const float* db = p.db + static_cast<long long>(copy) * p.n_frames * p.n_mels;
+    const int j0 = blockIdx.x * 64;
+    for (int idx = threadIdx.x; idx < 64 * p.n_mels; idx += blockDim.x) {
+        const int jj = idx / p.n_mels, f = idx % p.n_mels;
+        const int j = j0 + jj;
+        if (j >= p.out_t) continue;
+        float src = scale * (static_cast<float>(j) + 0.5f) - 0.5f;
+        if (src < 0.f) src = 0.f;
+        const int i0 = static_cast<int>(src);
+        const int i1 = i0 + (i0 < p.n_frames - 1 ? 1 : 0);
+        const float lam1 = src - static_cast<float>(i0), lam0 = 1.0f - lam1;
+        const float x0 = (fmaxf(db[static_cast<long long>(i0) * p.n_mels + f], fl) - mean) * inv;
+        const float x1 = (fmaxf(db[static_cast<long long>(i1) * p.n_mels + f], fl) - mean) * inv;
+        const __nv_bfloat16 o = __float2bfloat16_rn(lam0 * x0 + lam1 * x1);
+        p.img_t[(static_cast<long long>(copy) * p.out_t + j) * p.n_mels + f] = o;
+        s_tile[jj][f] = o;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * p.n_mels; idx += blockDim.x) {
+        const int f = idx / 64, jj = idx % 64;
+        const int j = j0 + jj;
+        if (j < p.out_t) p.img_f[(static_cast<long long>(copy) * p.n_mels + f) * p.ld_f + j] = s_tile[jj][f];
+    }
+}
+
+// y[b] = sum_i masks[b][i] * stems[i]  (LIME stem recombination, src/lime_explainer.py:283-301)
+__global__ void mix_stems_kernel(const float* __restrict__ stems, long long n_samples, int n_stems,
+                                 const unsigned char* __restrict__ masks, float* __restrict__ y, long long y_stride) {
+    const int copy = blockIdx.y;
+    for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < n_stems; ++s)
+            if (masks[copy * n_stems + s]) acc += stems[s * n_samples + i];
+        y[copy * y_stride + i] = acc;
+    }
+}
+
+}  // namespace b200x
+
+using namespace b200x;
+
+extern "C" int b200x_stft(const float* d_wave, int64_t n_samples, int n_fft, int hop, int reflect_pad, void* d_spec,
+                          int spec_stride, void* stream) {
+    B200X_REQUIRE(n_fft == NFFT && hop == HOP, "stft: only n_fft=2048, hop=512 are built (got %d/%d)", n_fft, hop);
+    B200X_REQUIRE(n_samples > NFFT / 2 && spec_stride >= NBIN, "stft: bad sizes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200X_TRY(ensure_tables(s));
+    static bool cfg = false;
+    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DSP_SMEM)); cfg = true; }
+    const int n_frames = 1 + static_cast<int>(n_samples / HOP);
+    const int grid = std::min(ceil_div(n_frames, DSP_WARPS), 148 * 8);
+    stft_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(d_wave, n_samples, n_frames, reflect_pad, reinterpret_cast<float2*>(d_spec), spec_stride);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_frames, int copies, int mode,
+                                  const int32_t* d_windows, float occlusion_value, const float* d_gains, float* d_y,
+                                  int64_t y_stride, double* d_sumsq, void* stream) {
+    B200X_REQUIRE(mode >= 0 && mode <= 3, "istft: bad mode %d", mode);
+    B200X_REQUIRE((mode != 1 && mode != 3) || d_windows != nullptr, "istft: windows missing");
+    B200X_REQUIRE(mode != 2 || d_gains != nullptr, "istft: gains missing");
+    B200X_REQUIRE(n_frames >= 2 && copies > 0, "istft: bad sizes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200X_TRY(ensure_tables(s));
+    static bool cfg = false;
+    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DSP_SMEM)); cfg = true; }
+    IstftParams p;
+    p.S = reinterpret_cast<const float2*>(d_spec); p.stride = spec_stride; p.n_frames = n_frames;
+    p.out_len = static_cast<long long>(HOP) * (n_frames - 1); p.out_stride = y_stride; p.y = d_y;
+    p.windows = d_windows; p.occlusion_value = occlusion_value; p.gains = d_gains; p.mode = mode;
+    p.hops_per_strip = 29; p.sumsq = d_sumsq;
+    B200X_REQUIRE(y_stride >= p.out_len, "istft: y_stride too small");
+    const int strips = ceil_div(n_frames - 1, p.hops_per_strip);
+    dim3 grid(ceil_div(strips, DSP_WARPS), copies);
+    istft_masked_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+namespace b200x {
+// HTK mel filterbank, torchaudio.functional.melscale_fbanks(norm=None, mel_scale='htk') restated; sparse rows.
+struct MelBank {
+    int n_mels = 0;
+    int *d_start = nullptr, *d_count = nullptr, *d_offset = nullptr;
+    float* d_weights = nullptr;
+};
+static MelBank g_bank;
+static double g_bank_key[4] = {0, 0, 0, 0};
+
+static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_max) {
+    if (g_bank.n_mels == n_mels && g_bank_key[0] == sample_rate && g_bank_key[1] == f_min && g_bank_key[2] == f_max)
+        return B200X_OK;
+    std::vector<double> f_pts(n_mels + 2);
+    const double m_min = 2595.0 * std::log10(1.0 + f_min / 700.0), m_max = 2595.0 * std::log10(1.0 + f_max / 700.0);
+    for (int i = 0; i < n_mels + 2; ++i) {
+        const double m = m_min + (m_max - m_min) * i / (n_mels + 1);
+        f_pts[i] = 700.0 * (std::pow(10.0, m / 2595.0) - 1.0);
+    }
+    std::vector<int> start(n_mels), count(n_mels), offset(n_mels);
+    std::vector<float> weights;
+    for (int f = 0; f < n_mels; ++f) {
+        int first = -1, last = -1;
+        std::vector<float> w(NBIN, 0.f);
+        for (int k = 0; k < NBIN; ++k) {
+            const double freq = static_cast<double>(k) * (sample_rate / 2) / (NBIN - 1);
+            const double down = (freq - f_pts[f]) / (f_pts[f + 1] - f_pts[f]);
+            const double up = (f_pts[f + 2] - freq) / (f_pts[f + 2] - f_pts[f + 1]);
+            const double v = std::max(0.0, std::min(down, up));
+            if (v > 0.0) { if (first < 0) first = k; last = k; w[k] = static_cast<float>(v); }
+        }
+        start[f] = first < 0 ? 0 : first;
+        count[f] = first < 0 ? 0 : last - first + 1;
+        offset[f] = static_cast<int>(weights.size());
+        for (int k = 0; k < count[f]; ++k) weights.push_back(w[start[f] + k]);
+    }
+    if (weights.empty()) weights.push_back(0.f);
+    if (g_bank.d_start) { cudaFree(g_bank.d_start); cudaFree(g_bank.d_count); cudaFree(g_bank.d_offset); cudaFree(g_bank.d_weights); }
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_start, n_mels * sizeof(int)));
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_count, n_mels * sizeof(int)));
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_offset, n_mels * sizeof(int)));
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_weights, weights.size() * sizeof(float)));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_start, start.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_count, count.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_offset, offset.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice));
+    g_bank.n_mels = n_mels;
+    g_bank_key[0] = sample_rate; g_bank_key[1] = f_min; g_bank_key[2] = f_max;
+    return B200X_OK;
+}
+}  // namespace b200x
+
+extern "C" int b200x_mel_frames_per_cta(void) { return 32; }
+
+extern "C" int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_samples, int copies, int sample_rate,
+                            int n_mels, double f_min, double f_max, double amin, const double* d_sumsq,
+                            double ref_rms, int64_t rms_count, float* d_db, float* d_cta_max, void* stream) {
+    B200X_REQUIRE(n_mels > 0 && n_mels <= 128 && n_mels % 32 == 0, "mel: n_mels=%d unsupported", n_mels);
+    B200X_REQUIRE(n_samples > NFFT / 2 && copies > 0, "mel: bad sizes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200X_TRY(ensure_tables(s));
+    B200X_TRY(ensure_melbank(sample_rate, n_mels, f_min, f_max));
+    static bool cfg = false;
+    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DSP_SMEM)); cfg = true; }
+    MelParams p;
+    p.y = d_y; p.y_stride = y_stride; p.n_samples = n_samples; p.sumsq = d_sumsq; p.ref_rms = ref_rms; p.rms_count = rms_count;
+    p.n_frames = 1 + static_cast<int>(n_samples / HOP); p.n_mels = n_mels;
+    p.fb_start = g_bank.d_start; p.fb_count = g_bank.d_count; p.fb_offset = g_bank.d_offset; p.fb_weights = g_bank.d_weights;
+    p.amin = static_cast<float>(amin); p.db = d_db; p.cta_max = d_cta_max; p.frames_per_cta = b200x_mel_frames_per_cta();
+    dim3 grid(ceil_div(p.n_frames, p.frames_per_cta), copies);
+    mel_db_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_mel_normalize_resize(const float* d_db, const float* d_cta_max, int n_cta_max, int copies,
+                                          int n_frames, int n_mels, float top_db, int unbiased, float eps, int out_t,
+                                          void* d_partial, float* d_floor, void* d_img_t, void* d_img_f, int ld_f,
+                                          void* stream) {
+    B200X_REQUIRE(n_mels <= 128 && (static_cast<long long>(n_frames) * n_mels) % 4 == 0, "resize: bad sizes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n_partial = 32;
+    dim3 g1(n_partial, copies);
+    mel_stats_kernel<<<g1, 256, 0, s>>>(d_db, static_cast<long long>(n_frames) * n_mels, d_cta_max, n_cta_max, top_db,
+                                        reinterpret_cast<double2*>(d_partial), d_floor);
+    B200X_CUDA_TRY(cudaGetLastError());
+    ResizeParams p;
+    p.db = d_db; p.partial = reinterpret_cast<const double2*>(d_partial); p.floor_val = d_floor; p.n_partial = n_partial;
+    p.n_frames = n_frames; p.n_mels = n_mels; p.out_t = out_t; p.unbiased = unbiased; p.eps = eps;
+    p.img_t = reinterpret_cast<__nv_bfloat16*>(d_img_t); p.img_f = reinterpret_cast<__nv_bfloat16*>(d_img_f); p.ld_f = ld_f;
+    dim3 g2(ceil_div(out_t, 64), copies);
+    mel_resize_kernel<<<g2, 256, 0, s>>>(p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_mix_stems(const float* d_stems, int64_t n_samples, int n_stems, const uint8_t* d_masks, int copies,
+                               float* d_y, int64_t y_stride, void* stream) {
+    B200X_REQUIRE(n_stems > 0 && copies > 0 && n_samples > 0, "mix_stems: bad sizes");
+    dim3 grid(296, copies);
+    mix_stems_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_stems, n_samples, n_stems, d_masks, d_y, y_stride);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}

@@ -1,0 +1,640 @@
+// Engine: host-side orchestration of the perturbation sweep behind the C ABI (include/b200xai.h).
+//
+// One engine per GPU / process.  Per track: wave and explainer STFT stay resident in HBM.  A sweep of N perturbed
+// copies is processed in chunks of `copies_per_chunk` so that the activation working set of the SpecTTTra forward
+// (residual stream fp32, LN output / qkv / attention / MLP hidden in bf16) stays resident in the 126 MB L2 while
+// the 12 encoder layers run over it; the perturbed spectrograms themselves are never materialised (the mask is
+// generated in the iSTFT load stage).  Everything is enqueued on one stream; no allocation in steady state.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+using namespace b200x;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = n;
+        if (n == 0) return B200X_OK;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) return set_error(B200X_ERR_CUDA, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+        return B200X_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LayerW {
+    DevBuf qkv_w, qkv_b, proj_w, proj_b, fc1_w, fc1_b, fc2_w, fc2_b, n1_g, n1_b, n2_g, n2_b;
+};
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// pick the UMMA N tile that wastes the fewest padded columns (ties -> wider tile)
+int pick_block_n(int n) {
+    const int cands[4] = {256, 208, 192, 128};
+    int best = 128, best_waste = 1 << 30;
+    for (int c : cands) {
+        const int waste = ceil_div(n, c) * c - n;
+        if (waste < best_waste) { best = c; best_waste = waste; }
+    }
+    return best;
+}
+
+}  // namespace
+
+struct b200x_engine {
+    b200x_model_config cfg;
+    int C = 0;                 // copies per chunk
+    int64_t max_samples = 0;
+    int T = 0, Tt = 0, Ts = 0; // tokens total / temporal / spectral
+    int D = 0, Hp = 0;         // embed dim, padded MLP hidden
+    bool finalized = false;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    std::map<std::string, std::vector<float>> params;
+
+    // packed weights
+    DevBuf tok_t_w, tok_s_w, tok_t_b, tok_s_b, pe_t, pe_s, np_t_g, np_t_b, np_s_g, np_s_b;
+    std::vector<LayerW> layers;
+    DevBuf fn_g, fn_b, cls_w;
+    float cls_b = 0.f;
+
+    // track state
+    int64_t L = 0;             // samples of the current track
+    int n_time = 0;
+    static constexpr int n_freq = 1025;
+    static constexpr int s_stride = 1028;
+    DevBuf wave, S;
+    double ref_rms = 0.0;      // sqrt(mean(wave^2) + 1e-8)
+
+    // workspace
+    int64_t y_stride = 0;
+    int max_frames = 0, n_cta_max = 0;
+    DevBuf y, db, cta_max, partial, floor_v, img_t, img_f, x, h, qkv, att, hid, head_part, prob, logit, sumsq;
+    DevBuf windows, gains, masks, stems, delta, order, map;
+    int last_copies = 0;
+    float* trace = nullptr;
+};
+
+namespace {
+
+int upload(DevBuf& b, const void* host, size_t bytes) {
+    B200X_TRY(b.alloc(bytes));
+    B200X_CUDA_TRY(cudaMemcpy(b.p, host, bytes, cudaMemcpyHostToDevice));
+    return B200X_OK;
+}
+
+int upload_bf16(DevBuf& b, const std::vector<float>& v) {
+    std::vector<__nv_bfloat16> t(v.size());
+    for (size_t i = 0; i < v.size(); ++i) t[i] = __float2bfloat16_rn(v[i]);
+    return upload(b, t.data(), t.size() * sizeof(__nv_bfloat16));
+}
+
+int get_param(b200x_engine* e, const std::string& name, size_t numel, const std::vector<float>** out) {
+    auto it = e->params.find(name);
+    if (it == e->params.end()) return set_error(B200X_ERR_STATE, "missing parameter '%s'", name.c_str());
+    if (it->second.size() != numel)
+        return set_error(B200X_ERR_INVALID, "parameter '%s' has %zu elements, expected %zu", name.c_str(), it->second.size(), numel);
+    *out = &it->second;
+    return B200X_OK;
+}
+
+int ensure_grow(DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return B200X_OK;
+    return b.alloc(bytes);
+}
+
+// The SpecTTTra forward over `copies` waves already sitting in e->y (rows of y_stride floats, n_samples valid).
+int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* d_sumsq, int64_t rms_count, float* d_prob,
+                  float* d_logit) {
+    const b200x_model_config& c = e->cfg;
+    cudaStream_t s = e->stream;
+    const int n_frames = 1 + static_cast<int>(n_samples / c.hop_length);
+    const int n_cta = ceil_div(n_frames, b200x_mel_frames_per_cta());
+    const int D = e->D, T = e->T, M = copies * T;
+    e->last_copies = copies;
+    B200X_TRY(b200x_mel_db(e->y.as<float>(), e->y_stride, n_samples, copies, c.sample_rate, c.n_mels, c.f_min, c.f_max, c.amin,
+                           d_sumsq, e->ref_rms, rms_count, e->db.as<float>(), e->cta_max.as<float>(), s));
+    B200X_TRY(b200x_mel_normalize_resize(e->db.as<float>(), e->cta_max.as<float>(), n_cta, copies, n_frames, c.n_mels,
+                                         static_cast<float>(c.top_db), c.std_unbiased, c.norm_eps, c.input_temp_dim,
+                                         e->partial.p, e->floor_v.as<float>(), e->img_t.p, e->img_f.p, c.input_temp_dim, s));
+    e->launches += 3;
+    // tokenizers: temporal rows = t_clip consecutive time steps x n_mels; spectral rows = one mel row over time
+    const int Kt = c.t_clip * c.input_spec_dim;
+    B200X_TRY(b200x_gemm_bf16(e->img_t.p, Kt, e->tok_t_w.p, Kt, copies * e->Tt, D, Kt, pick_block_n(D), e->x.p, D,
+                              B200X_GEMM_OUT_F32_TOKEN, e->tok_t_b.as<float>(), 1, nullptr, e->pe_t.as<float>(), e->Tt, T, 0, s));
+    B200X_TRY(b200x_gemm_bf16(e->img_f.p, c.input_temp_dim, e->tok_s_w.p, c.input_temp_dim, copies * e->Ts, D,
+                              c.input_temp_dim, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_TOKEN, e->tok_s_b.as<float>(), 1,
+                              nullptr, e->pe_s.as<float>(), e->Ts, T, e->Tt, s));
+    e->launches += 2;
+    if (c.pre_norm) {
+        B200X_TRY(b200x_layernorm(e->x.as<float>(), M, D, e->np_t_g.as<float>(), e->np_t_b.as<float>(), e->np_s_g.as<float>(),
+                                  e->np_s_b.as<float>(), T, e->Tt, c.tokenizer_ln_eps, nullptr, e->x.as<float>(), s));
+        e->launches += 1;
+    }
+    const size_t xbytes = static_cast<size_t>(M) * D * sizeof(float);
+    if (e->trace) B200X_CUDA_TRY(cudaMemcpyAsync(e->trace, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
+    for (int l = 0; l < c.num_layers; ++l) {
+        LayerW& w = e->layers[l];
+        B200X_TRY(b200x_layernorm(e->x.as<float>(), M, D, w.n1_g.as<float>(), w.n1_b.as<float>(), nullptr, nullptr, 0, 0,
+                                  c.block_ln_eps, e->h.p, nullptr, s));
+        B200X_TRY(b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
+                                  c.qkv_bias ? w.qkv_b.as<float>() : nullptr, 0, nullptr, nullptr, 0, 0, 0, s));
+        B200X_TRY(b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, s));
+        B200X_TRY(b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
+                                  w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
+        B200X_TRY(b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
+                                  c.block_ln_eps, e->h.p, nullptr, s));
+        B200X_TRY(b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
+                                  w.fc1_b.as<float>(), 1, nullptr, nullptr, 0, 0, 0, s));
+        B200X_TRY(b200x_gemm_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, pick_block_n(D), e->x.p, D,
+                                  B200X_GEMM_OUT_F32_RESID, w.fc2_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
+        e->launches += 7;
+        if (e->trace)
+            B200X_CUDA_TRY(cudaMemcpyAsync(e->trace + static_cast<size_t>(l + 1) * M * D, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
+    }
+    B200X_TRY(b200x_head(e->x.as<float>(), copies, T, D, e->fn_g.as<float>(), e->fn_b.as<float>(), c.block_ln_eps, c.final_norm,
+                         e->cls_w.as<float>(), e->cls_b, e->head_part.as<float>(), d_logit, d_prob, s));
+    e->launches += 2;
+    return B200X_OK;
+}
+
+int check_ready(b200x_engine* e, bool need_track) {
+    if (e == nullptr) return set_error(B200X_ERR_INVALID, "engine is NULL");
+    if (!e->finalized) return set_error(B200X_ERR_STATE, "engine weights not finalized");
+    if (need_track && e->L == 0) return set_error(B200X_ERR_STATE, "no track loaded (call b200x_engine_set_track)");
+    return B200X_OK;
+}
+
+int ensure_prob(b200x_engine* e, int n) {
+    B200X_TRY(ensure_grow(e->prob, static_cast<size_t>(std::max(n, 1)) * sizeof(float)));
+    B200X_TRY(ensure_grow(e->logit, static_cast<size_t>(std::max(n, 1)) * sizeof(float)));
+    return B200X_OK;
+}
+
+}  // namespace
+
+extern "C" int b200x_engine_create(const b200x_model_config* cfg, int copies_per_chunk, int64_t max_samples,
+                                   b200x_engine** out) {
+    B200X_REQUIRE(cfg != nullptr && out != nullptr, "engine_create: NULL argument");
+    B200X_REQUIRE(cfg->n_fft == 2048 && cfg->hop_length == 512, "engine: only n_fft=2048 / hop=512 kernels are built");
+    B200X_REQUIRE(cfg->embed_dim % 128 == 0 && cfg->embed_dim / cfg->num_heads == 64, "engine: embed_dim must be a multiple of 128 with head_dim 64");
+    B200X_REQUIRE(cfg->f_clip == 1, "engine: f_clip=%d unsupported (alpha variant uses 1)", cfg->f_clip);
+    B200X_REQUIRE(cfg->input_spec_dim == cfg->n_mels, "engine: input_spec_dim must equal n_mels (no resize along mel axis)");
+    B200X_REQUIRE((cfg->t_clip * cfg->input_spec_dim) % 8 == 0 && cfg->input_temp_dim % 8 == 0, "engine: tokenizer K not 16-byte aligned");
+    B200X_REQUIRE(copies_per_chunk >= 1 && copies_per_chunk <= 256, "engine: copies_per_chunk out of range");
+    B200X_REQUIRE(max_samples >= 4096, "engine: max_samples too small");
+    int dev = 0, major = 0;
+    B200X_CUDA_TRY(cudaGetDevice(&dev));
+    B200X_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    B200X_REQUIRE(major == 10, "engine: this library contains sm_100a code only (device has compute capability %d.x)", major);
+    b200x_engine* e = new b200x_engine();
+    e->cfg = *cfg;
+    e->C = copies_per_chunk;
+    e->max_samples = max_samples;
+    e->Tt = (cfg->input_temp_dim - cfg->t_clip) / cfg->t_clip + 1;
+    e->Ts = (cfg->input_spec_dim - cfg->f_clip) / cfg->f_clip + 1;
+    e->T = e->Tt + e->Ts;
+    e->D = cfg->embed_dim;
+    e->Hp = round_up(cfg->mlp_hidden, 16);
+    if (e->T % 16 != 0) { delete e; return set_error(B200X_ERR_INVALID, "engine: token count %d must be a multiple of 16", e->T); }
+    cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { delete e; return set_error(B200X_ERR_CUDA, "stream create failed: %s", cudaGetErrorString(ce)); }
+    const int C = e->C, D = e->D, T = e->T;
+    const size_t M = static_cast<size_t>(C) * T;
+    e->y_stride = (max_samples + 7) / 8 * 8;
+    e->max_frames = 1 + static_cast<int>(max_samples / cfg->hop_length);
+    e->n_cta_max = ceil_div(e->max_frames, b200x_mel_frames_per_cta());
+    int st = B200X_OK;
+    auto A = [&](DevBuf& b, size_t bytes) { if (st == B200X_OK) st = b.alloc(bytes); };
+    A(e->y, static_cast<size_t>(C) * e->y_stride * sizeof(float));
+    A(e->db, static_cast<size_t>(C) * e->max_frames * cfg->n_mels * sizeof(float));
+    A(e->cta_max, static_cast<size_t>(C) * e->n_cta_max * sizeof(float));
+    A(e->partial, static_cast<size_t>(C) * 32 * 2 * sizeof(double));
+    A(e->floor_v, static_cast<size_t>(C) * sizeof(float));
+    A(e->img_t, static_cast<size_t>(C) * cfg->input_temp_dim * cfg->n_mels * 2);
+    A(e->img_f, static_cast<size_t>(C) * cfg->n_mels * cfg->input_temp_dim * 2);
+    A(e->x, M * D * sizeof(float));
+    A(e->h, M * D * 2);
+    A(e->qkv, M * 3 * D * 2);
+    A(e->att, M * D * 2);
+    A(e->hid, M * e->Hp * 2);
+    A(e->head_part, static_cast<size_t>(C) * b200x_head_slices() * sizeof(float));
+    A(e->sumsq, static_cast<size_t>(C) * sizeof(double));
+    A(e->wave, static_cast<size_t>(e->y_stride) * sizeof(float));
+    A(e->S, static_cast<size_t>(e->max_frames) * b200x_engine::s_stride * 2 * sizeof(float));
+    if (st != B200X_OK) { b200x_engine_destroy(e); return st; }
+    cudaMemset(e->y.p, 0, e->y.bytes);
+    *out = e;
+    return B200X_OK;
+}
+
+extern "C" void b200x_engine_destroy(b200x_engine* e) {
+    if (!e) return;
+    DevBuf* bufs[] = {&e->tok_t_w, &e->tok_s_w, &e->tok_t_b, &e->tok_s_b, &e->pe_t, &e->pe_s, &e->np_t_g, &e->np_t_b, &e->np_s_g,
+                      &e->np_s_b, &e->fn_g, &e->fn_b, &e->cls_w, &e->wave, &e->S, &e->y, &e->db, &e->cta_max, &e->partial,
+                      &e->floor_v, &e->img_t, &e->img_f, &e->x, &e->h, &e->qkv, &e->att, &e->hid, &e->head_part, &e->prob,
+                      &e->logit, &e->sumsq, &e->windows, &e->gains, &e->masks, &e->stems, &e->delta, &e->order, &e->map};
+    for (DevBuf* b : bufs) b->release();
+    for (LayerW& w : e->layers) {
+        DevBuf* lb[] = {&w.qkv_w, &w.qkv_b, &w.proj_w, &w.proj_b, &w.fc1_w, &w.fc1_b, &w.fc2_w, &w.fc2_b, &w.n1_g, &w.n1_b, &w.n2_g, &w.n2_b};
+        for (DevBuf* b : lb) b->release();
+    }
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int b200x_engine_set_param(b200x_engine* e, const char* name, const float* data, int64_t numel) {
+    B200X_REQUIRE(e && name && data && numel > 0, "set_param: bad argument");
+    e->params[name] = std::vector<float>(data, data + numel);
+    e->finalized = false;
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_finalize(b200x_engine* e) {
+    B200X_REQUIRE(e != nullptr, "finalize: engine is NULL");
+    const b200x_model_config& c = e->cfg;
+    const int D = e->D, F = c.input_spec_dim, Tm = c.input_temp_dim, H = c.mlp_hidden, Hp = e->Hp;
+    const std::vector<float>* p = nullptr;
+    const std::string tk = "encoder.st_tokenizer.";
+    // temporal conv weight [D][F][t_clip] -> [D][t_clip * F], K index = k * F + f (matches img_t rows)
+    B200X_TRY(get_param(e, tk + "temporal_tokenizer.conv1d.weight", static_cast<size_t>(D) * F * c.t_clip, &p));
+    {
+        std::vector<float> w(static_cast<size_t>(D) * c.t_clip * F);
+        for (int o = 0; o < D; ++o)
+            for (int f = 0; f < F; ++f)
+                for (int k = 0; k < c.t_clip; ++k)
+                    w[(static_cast<size_t>(o) * c.t_clip + k) * F + f] = (*p)[(static_cast<size_t>(o) * F + f) * c.t_clip + k];
+        B200X_TRY(upload_bf16(e->tok_t_w, w));
+    }
+    B200X_TRY(get_param(e, tk + "spectral_tokenizer.conv1d.weight", static_cast<size_t>(D) * Tm * c.f_clip, &p));
+    B200X_TRY(upload_bf16(e->tok_s_w, *p));
+    std::vector<float> zeros_d(D, 0.f), ones_d(D, 1.f);
+    if (!c.pre_norm) {
+        B200X_TRY(get_param(e, tk + "temporal_tokenizer.conv1d.bias", D, &p));
+        B200X_TRY(upload(e->tok_t_b, p->data(), D * sizeof(float)));
+        B200X_TRY(get_param(e, tk + "spectral_tokenizer.conv1d.bias", D, &p));
+        B200X_TRY(upload(e->tok_s_b, p->data(), D * sizeof(float)));
+    } else {
+        B200X_TRY(upload(e->tok_t_b, zeros_d.data(), D * sizeof(float)));
+        B200X_TRY(upload(e->tok_s_b, zeros_d.data(), D * sizeof(float)));
+        B200X_TRY(get_param(e, tk + "temporal_tokenizer.norm_pre.weight", D, &p)); B200X_TRY(upload(e->np_t_g, p->data(), D * 4));
+        B200X_TRY(get_param(e, tk + "temporal_tokenizer.norm_pre.bias", D, &p));   B200X_TRY(upload(e->np_t_b, p->data(), D * 4));
+        B200X_TRY(get_param(e, tk + "spectral_tokenizer.norm_pre.weight", D, &p)); B200X_TRY(upload(e->np_s_g, p->data(), D * 4));
+        B200X_TRY(get_param(e, tk + "spectral_tokenizer.norm_pre.bias", D, &p));   B200X_TRY(upload(e->np_s_b, p->data(), D * 4));
+    }
+    if (c.pe_learnable) {
+        B200X_TRY(get_param(e, tk + "temporal_tokenizer.pos_encoder.pe", static_cast<size_t>(e->Tt) * D, &p));
+        B200X_TRY(upload(e->pe_t, p->data(), p->size() * 4));
+        B200X_TRY(get_param(e, tk + "spectral_tokenizer.pos_encoder.pe", static_cast<size_t>(e->Ts) * D, &p));
+        B200X_TRY(upload(e->pe_s, p->data(), p->size() * 4));
+    } else {                                   // sinusoidal encoding, computed here in float32 like torch
+        for (int which = 0; which < 2; ++which) {
+            const int n = which == 0 ? e->Tt : e->Ts;
+            std::vector<float> pe(static_cast<size_t>(n) * D, 0.f);
+            for (int pos = 0; pos < n; ++pos)
+                for (int i = 0; i < D; i += 2) {
+                    const float div = std::exp(static_cast<float>(i) * static_cast<float>(-std::log(10000.0) / D));
+                    pe[static_cast<size_t>(pos) * D + i] = std::sin(pos * div);
+                    if (i + 1 < D) pe[static_cast<size_t>(pos) * D + i + 1] = std::cos(pos * div);
+                }
+            B200X_TRY(upload(which == 0 ? e->pe_t : e->pe_s, pe.data(), pe.size() * 4));
+        }
+    }
+    e->layers.clear();
+    e->layers.resize(c.num_layers);
+    for (int l = 0; l < c.num_layers; ++l) {
+        LayerW& w = e->layers[l];
+        const std::string b = "encoder.transformer.blocks." + std::to_string(l) + ".";
+        B200X_TRY(get_param(e, b + "norm1.weight", D, &p)); B200X_TRY(upload(w.n1_g, p->data(), D * 4));
+        B200X_TRY(get_param(e, b + "norm1.bias", D, &p));   B200X_TRY(upload(w.n1_b, p->data(), D * 4));
+        B200X_TRY(get_param(e, b + "norm2.weight", D, &p)); B200X_TRY(upload(w.n2_g, p->data(), D * 4));
+        B200X_TRY(get_param(e, b + "norm2.bias", D, &p));   B200X_TRY(upload(w.n2_b, p->data(), D * 4));
+        B200X_TRY(get_param(e, b + "attn.qkv.weight", static_cast<size_t>(3) * D * D, &p)); B200X_TRY(upload_bf16(w.qkv_w, *p));
+        if (c.qkv_bias) { B200X_TRY(get_param(e, b + "attn.qkv.bias", 3 * D, &p)); B200X_TRY(upload(w.qkv_b, p->data(), 3 * D * 4)); }
+        B200X_TRY(get_param(e, b + "attn.proj.weight", static_cast<size_t>(D) * D, &p)); B200X_TRY(upload_bf16(w.proj_w, *p));
+        B200X_TRY(get_param(e, b + "attn.proj.bias", D, &p)); B200X_TRY(upload(w.proj_b, p->data(), D * 4));
+        // MLP hidden padded to a multiple of 16 with zero rows / columns (GELU(0) = 0 keeps the padding inert)
+        B200X_TRY(get_param(e, b + "mlp.fc1.weight", static_cast<size_t>(H) * D, &p));
+        { std::vector<float> t(static_cast<size_t>(Hp) * D, 0.f); std::copy(p->begin(), p->end(), t.begin()); B200X_TRY(upload_bf16(w.fc1_w, t)); }
+        B200X_TRY(get_param(e, b + "mlp.fc1.bias", H, &p));
+        { std::vector<float> t(Hp, 0.f); std::copy(p->begin(), p->end(), t.begin()); B200X_TRY(upload(w.fc1_b, t.data(), Hp * 4)); }
+        B200X_TRY(get_param(e, b + "mlp.fc2.weight", static_cast<size_t>(D) * H, &p));
+        { std::vector<float> t(static_cast<size_t>(D) * Hp, 0.f);
+          for (int o = 0; o < D; ++o) std::copy(p->begin() + static_cast<size_t>(o) * H, p->begin() + static_cast<size_t>(o + 1) * H, t.begin() + static_cast<size_t>(o) * Hp);
+          B200X_TRY(upload_bf16(w.fc2_w, t)); }
+        B200X_TRY(get_param(e, b + "mlp.fc2.bias", D, &p)); B200X_TRY(upload(w.fc2_b, p->data(), D * 4));
+    }
+    if (c.final_norm) {
+        B200X_TRY(get_param(e, "encoder.transformer.norm.weight", D, &p)); B200X_TRY(upload(e->fn_g, p->data(), D * 4));
+        B200X_TRY(get_param(e, "encoder.transformer.norm.bias", D, &p));   B200X_TRY(upload(e->fn_b, p->data(), D * 4));
+    } else {
+        B200X_TRY(upload(e->fn_g, ones_d.data(), D * 4));
+        B200X_TRY(upload(e->fn_b, zeros_d.data(), D * 4));
+    }
+    B200X_TRY(get_param(e, "classifier.weight", D, &p)); B200X_TRY(upload(e->cls_w, p->data(), D * 4));
+    B200X_TRY(get_param(e, "classifier.bias", 1, &p));
+    e->cls_b = (*p)[0];
+    e->params.clear();
+    e->finalized = true;
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_predict(b200x_engine* e, const float* waves, int64_t n_samples, int count, int on_device,
+                                    float* prob, float* logit) {
+    B200X_TRY(check_ready(e, false));
+    B200X_REQUIRE(waves && prob && count > 0, "predict: bad argument");
+    B200X_REQUIRE(n_samples > 1024 && n_samples <= e->max_samples, "predict: n_samples=%lld outside (1024, %lld]", (long long)n_samples, (long long)e->max_samples);
+    B200X_TRY(ensure_prob(e, count));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int c0 = 0; c0 < count; c0 += e->C) {
+        const int n = std::min(e->C, count - c0);
+        B200X_CUDA_TRY(cudaMemcpy2DAsync(e->y.p, e->y_stride * sizeof(float), waves + static_cast<size_t>(c0) * n_samples,
+                                         n_samples * sizeof(float), n_samples * sizeof(float), n, kind, e->stream));
+        B200X_TRY(forward_chunk(e, n, n_samples, nullptr, 0, e->prob.as<float>() + c0, e->logit.as<float>() + c0));
+    }
+    const cudaMemcpyKind back = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, count * sizeof(float), back, e->stream));
+    if (logit) B200X_CUDA_TRY(cudaMemcpyAsync(logit, e->logit.p, count * sizeof(float), back, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_set_track(b200x_engine* e, const float* wave, int64_t n_samples, int on_device) {
+    B200X_TRY(check_ready(e, false));
+    B200X_REQUIRE(wave != nullptr, "set_track: wave is NULL");
+    B200X_REQUIRE(n_samples >= 2048 && n_samples <= e->max_samples, "set_track: n_samples=%lld outside [2048, %lld]", (long long)n_samples, (long long)e->max_samples);
+    B200X_CUDA_TRY(cudaMemcpyAsync(e->wave.p, wave, n_samples * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    e->L = n_samples;
+    e->n_time = 1 + static_cast<int>(n_samples / e->cfg.hop_length);
+    B200X_TRY(b200x_stft(e->wave.as<float>(), n_samples, e->cfg.n_fft, e->cfg.hop_length, 0, e->S.p, b200x_engine::s_stride, e->stream));
+    e->launches += 1;
+    // reference RMS for match_rms: sqrt(mean(sig^2) + 1e-8), float64 on the host like the reference (needs the host copy)
+    std::vector<float> tmp;
+    const float* hw = wave;
+    if (on_device) {
+        tmp.resize(n_samples);
+        B200X_CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->wave.p, n_samples * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        hw = tmp.data();
+    }
+    double acc = 0.0;
+    for (int64_t i = 0; i < n_samples; ++i) { const float v = hw[i]; acc += static_cast<double>(v * v); }
+    e->ref_rms = std::sqrt(acc / static_cast<double>(n_samples) + 1e-8);
+    // the tail of every y row beyond hop*(n_time-1) must read as zero padding (spectrogram_explainability.py:679-680)
+    B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, e->y.bytes, e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_track_shape(b200x_engine* e, int32_t* n_freq, int32_t* n_time) {
+    B200X_TRY(check_ready(e, true));
+    if (n_freq) *n_freq = b200x_engine::n_freq;
+    if (n_time) *n_time = e->n_time;
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_get_spectrogram(b200x_engine* e, float* spec_host) {
+    B200X_TRY(check_ready(e, true));
+    B200X_REQUIRE(spec_host != nullptr, "get_spectrogram: NULL output");
+    std::vector<float> tmp(static_cast<size_t>(e->n_time) * b200x_engine::s_stride * 2);
+    B200X_CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->S.p, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    const int F = b200x_engine::n_freq, Tn = e->n_time;
+    for (int t = 0; t < Tn; ++t)
+        for (int f = 0; f < F; ++f) {
+            spec_host[(static_cast<size_t>(f) * Tn + t) * 2] = tmp[(static_cast<size_t>(t) * b200x_engine::s_stride + f) * 2];
+            spec_host[(static_cast<size_t>(f) * Tn + t) * 2 + 1] = tmp[(static_cast<size_t>(t) * b200x_engine::s_stride + f) * 2 + 1];
+        }
+    return B200X_OK;
+}
+
+namespace {
+// shared body of the occlusion / FBP sweeps: perturb in the iSTFT load stage, classify, collect probabilities
+int sweep(b200x_engine* e, int mode, int n, const int32_t* d_windows, float occ_value, const float* d_gains, bool rms,
+          float* d_prob_out) {
+    const int64_t out_len = static_cast<int64_t>(e->cfg.hop_length) * (e->n_time - 1);
+    for (int c0 = 0; c0 < n; c0 += e->C) {
+        const int m = std::min(e->C, n - c0);
+        double* sumsq = nullptr;
+        if (rms) {
+            sumsq = e->sumsq.as<double>();
+            B200X_CUDA_TRY(cudaMemsetAsync(sumsq, 0, m * sizeof(double), e->stream));
+        }
+        B200X_TRY(b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, d_windows ? d_windows + 4 * c0 : nullptr,
+                                     occ_value, d_gains ? d_gains + static_cast<size_t>(c0) * b200x_engine::n_freq : nullptr,
+                                     e->y.as<float>(), e->y_stride, sumsq, e->stream));
+        e->launches += 1;
+        // occlusion: the reference pads/trims y_occ to len(y); FBP feeds the iSTFT output as is (dsp_band_ops.py:580-586)
+        const int64_t n_cls = (mode == B200X_MASK_BAND_GAIN) ? out_len : e->L;
+        if (n_cls > out_len)   // zero padding of the tail (spectrogram_explainability.py:679-680)
+            B200X_CUDA_TRY(cudaMemset2DAsync(e->y.as<float>() + out_len, e->y_stride * sizeof(float), 0,
+                                             (n_cls - out_len) * sizeof(float), m, e->stream));
+        B200X_TRY(forward_chunk(e, m, n_cls, sumsq, out_len, d_prob_out + c0, e->logit.as<float>() + c0));
+    }
+    return B200X_OK;
+}
+}  // namespace
+
+extern "C" int b200x_engine_occlusion_sweep(b200x_engine* e, const int32_t* windows, int n, float occlusion_value,
+                                            int on_device, float* prob) {
+    B200X_TRY(check_ready(e, true));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(windows && prob && n > 0, "occlusion_sweep: bad argument");
+    B200X_TRY(ensure_prob(e, n));
+    const int32_t* d_win = windows;
+    if (!on_device) {
+        for (int i = 0; i < n; ++i) {
+            const int32_t* w = windows + 4 * i;
+            B200X_REQUIRE(w[0] >= 0 && w[0] <= w[1] && w[1] <= e->n_time && w[2] >= 0 && w[2] <= w[3] && w[3] <= b200x_engine::n_freq,
+                          "occlusion_sweep: window %d = (%d,%d,%d,%d) outside the %dx%d spectrogram", i, w[0], w[1], w[2], w[3],
+                          b200x_engine::n_freq, e->n_time);
+        }
+        B200X_TRY(ensure_grow(e->windows, static_cast<size_t>(n) * 4 * sizeof(int32_t)));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, windows, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, e->stream));
+        d_win = e->windows.as<int32_t>();
+    }
+    B200X_TRY(sweep(e, B200X_MASK_OCCLUDE, n, d_win, occlusion_value, nullptr, false, e->prob.as<float>()));
+    B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_fbp_sweep(b200x_engine* e, const float* gains, int n, int normalize_loudness, int on_device,
+                                      float* prob) {
+    B200X_TRY(check_ready(e, true));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(gains && prob && n > 0, "fbp_sweep: bad argument");
+    B200X_TRY(ensure_prob(e, n));
+    const float* d_g = gains;
+    if (!on_device) {
+        const size_t bytes = static_cast<size_t>(n) * b200x_engine::n_freq * sizeof(float);
+        B200X_TRY(ensure_grow(e->gains, bytes));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->gains.p, gains, bytes, cudaMemcpyHostToDevice, e->stream));
+        d_g = e->gains.as<float>();
+    }
+    B200X_TRY(sweep(e, B200X_MASK_BAND_GAIN, n, nullptr, 0.f, d_g, normalize_loudness != 0, e->prob.as<float>()));
+    B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_stem_sweep(b200x_engine* e, const float* stems, int n_stems, int64_t n_samples,
+                                       const uint8_t* masks, int n, int on_device, float* prob) {
+    B200X_TRY(check_ready(e, false));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(stems && masks && prob && n > 0 && n_stems > 0, "stem_sweep: bad argument");
+    B200X_REQUIRE(n_samples > 1024 && n_samples <= e->max_samples, "stem_sweep: n_samples out of range");
+    B200X_TRY(ensure_prob(e, n));
+    const float* d_st = stems;
+    const uint8_t* d_mk = masks;
+    if (!on_device) {
+        const size_t sb = static_cast<size_t>(n_stems) * n_samples * sizeof(float);
+        B200X_TRY(ensure_grow(e->stems, sb));
+        B200X_TRY(ensure_grow(e->masks, static_cast<size_t>(n) * n_stems));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->stems.p, stems, sb, cudaMemcpyHostToDevice, e->stream));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->masks.p, masks, static_cast<size_t>(n) * n_stems, cudaMemcpyHostToDevice, e->stream));
+        d_st = e->stems.as<float>();
+        d_mk = e->masks.as<uint8_t>();
+    }
+    for (int c0 = 0; c0 < n; c0 += e->C) {
+        const int m = std::min(e->C, n - c0);
+        B200X_TRY(b200x_mix_stems(d_st, n_samples, n_stems, d_mk + static_cast<size_t>(c0) * n_stems, m, e->y.as<float>(), e->y_stride, e->stream));
+        e->launches += 1;
+        B200X_TRY(forward_chunk(e, m, n_samples, nullptr, 0, e->prob.as<float>() + c0, e->logit.as<float>() + c0));
+    }
+    B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+namespace {
+int audio_out(b200x_engine* e, int mode, const int32_t* windows, const float* gains, int n, float* audio_host) {
+    const int64_t out_len = static_cast<int64_t>(e->cfg.hop_length) * (e->n_time - 1);
+    if (windows) {
+        B200X_TRY(ensure_grow(e->windows, static_cast<size_t>(n) * 16));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, windows, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (gains) {
+        const size_t bytes = static_cast<size_t>(n) * b200x_engine::n_freq * sizeof(float);
+        B200X_TRY(ensure_grow(e->gains, bytes));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->gains.p, gains, bytes, cudaMemcpyHostToDevice, e->stream));
+    }
+    for (int c0 = 0; c0 < n; c0 += e->C) {
+        const int m = std::min(e->C, n - c0);
+        B200X_TRY(b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, windows ? e->windows.as<int32_t>() + 4 * c0 : nullptr,
+                                     0.f, gains ? e->gains.as<float>() + static_cast<size_t>(c0) * b200x_engine::n_freq : nullptr,
+                                     e->y.as<float>(), e->y_stride, nullptr, e->stream));
+        e->launches += 1;
+        B200X_CUDA_TRY(cudaMemcpy2DAsync(audio_host + static_cast<size_t>(c0) * out_len, out_len * sizeof(float), e->y.p,
+                                         e->y_stride * sizeof(float), out_len * sizeof(float), m, cudaMemcpyDeviceToHost, e->stream));
+    }
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+}  // namespace
+
+extern "C" int b200x_engine_window_audio(b200x_engine* e, const int32_t* windows, int n, float* audio_host) {
+    B200X_TRY(check_ready(e, true));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(windows && audio_host && n > 0, "window_audio: bad argument");
+    return audio_out(e, B200X_MASK_KEEP_ONLY, windows, nullptr, n, audio_host);
+}
+
+extern "C" int b200x_engine_band_audio(b200x_engine* e, const float* gains, int n, float* audio_host) {
+    B200X_TRY(check_ready(e, true));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(gains && audio_host && n > 0, "band_audio: bad argument");
+    return audio_out(e, B200X_MASK_BAND_GAIN, nullptr, gains, n, audio_host);
+}
+
+extern "C" int b200x_engine_saliency_map(b200x_engine* e, const int32_t* windows, const double* delta, int n,
+                                         double* map_host) {
+    B200X_TRY(check_ready(e, true));
+    B200X_REQUIRE(map_host && n >= 0 && (n == 0 || (windows && delta)), "saliency_map: bad argument");
+    const size_t cells = static_cast<size_t>(b200x_engine::n_freq) * e->n_time;
+    B200X_TRY(ensure_grow(e->map, cells * sizeof(double)));
+    B200X_TRY(ensure_grow(e->windows, static_cast<size_t>(std::max(n, 1)) * 16));
+    B200X_TRY(ensure_grow(e->delta, static_cast<size_t>(std::max(n, 1)) * sizeof(double)));
+    if (n > 0) {
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, windows, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, e->stream));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->delta.p, delta, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    B200X_TRY(b200x_saliency_reduce(e->windows.as<int32_t>(), e->delta.as<double>(), n, b200x_engine::n_freq, e->n_time, e->map.as<double>(), e->stream));
+    e->launches += 1;
+    B200X_CUDA_TRY(cudaMemcpyAsync(map_host, e->map.p, cells * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_band_map(b200x_engine* e, const int32_t* band_rows, const double* delta, int n,
+                                     double* map_host) {
+    B200X_TRY(check_ready(e, true));
+    B200X_REQUIRE(map_host && n >= 0 && (n == 0 || (band_rows && delta)), "band_map: bad argument");
+    const size_t cells = static_cast<size_t>(b200x_engine::n_freq) * e->n_time;
+    B200X_TRY(ensure_grow(e->map, cells * sizeof(double)));
+    B200X_TRY(ensure_grow(e->windows, static_cast<size_t>(std::max(n, 1)) * 8));
+    B200X_TRY(ensure_grow(e->delta, static_cast<size_t>(std::max(n, 1)) * sizeof(double)));
+    if (n > 0) {
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, band_rows, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, e->stream));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->delta.p, delta, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    B200X_TRY(b200x_band_map(e->windows.as<int32_t>(), e->delta.as<double>(), n, b200x_engine::n_freq, e->n_time, e->map.as<double>(), e->stream));
+    e->launches += 1;
+    B200X_CUDA_TRY(cudaMemcpyAsync(map_host, e->map.p, cells * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_rank(b200x_engine* e, const double* values, int n, int mode, int32_t* order_host) {
+    B200X_REQUIRE(e != nullptr, "rank: engine is NULL");
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(values && order_host && n > 0, "rank: bad argument");
+    B200X_TRY(ensure_grow(e->delta, static_cast<size_t>(n) * sizeof(double)));
+    B200X_TRY(ensure_grow(e->order, static_cast<size_t>(n) * sizeof(int32_t)));
+    B200X_CUDA_TRY(cudaMemcpyAsync(e->delta.p, values, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    B200X_TRY(b200x_rank(e->delta.as<double>(), n, mode, e->order.as<int32_t>(), e->stream));
+    e->launches += 1;
+    B200X_CUDA_TRY(cudaMemcpyAsync(order_host, e->order.p, static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_debug_buffer(b200x_engine* e, const char* name, void** d_ptr, int64_t* bytes) {
+    B200X_REQUIRE(e && name && d_ptr, "debug_buffer: bad argument");
+    const std::string n(name);
+    DevBuf* b = nullptr;
+    if (n == "y") b = &e->y; else if (n == "db") b = &e->db; else if (n == "img_t") b = &e->img_t;
+    else if (n == "img_f") b = &e->img_f; else if (n == "x") b = &e->x; else if (n == "h") b = &e->h;
+    else if (n == "qkv") b = &e->qkv; else if (n == "att") b = &e->att; else if (n == "hid") b = &e->hid;
+    else if (n == "prob") b = &e->prob; else if (n == "logit") b = &e->logit; else if (n == "S") b = &e->S;
+    else if (n == "wave") b = &e->wave;
+    else return set_error(B200X_ERR_INVALID, "debug_buffer: unknown buffer '%s'", name);
+    *d_ptr = b->p;
+    if (bytes) *bytes = static_cast<int64_t>(b->bytes);
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_set_trace(b200x_engine* e, float* d_trace) {
+    B200X_REQUIRE(e != nullptr, "set_trace: engine is NULL");
+    e->trace = d_trace;
+    return B200X_OK;
+}
+
+extern "C" int64_t b200x_engine_launch_count(b200x_engine* e) { return e ? e->launches : -1; }
+extern "C" void* b200x_engine_stream(b200x_engine* e) { return e ? static_cast<void*>(e->stream) : nullptr; }
+extern "C" int b200x_engine_synchronize(b200x_engine* e) {
+    B200X_REQUIRE(e != nullptr, "synchronize: engine is NULL");
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}

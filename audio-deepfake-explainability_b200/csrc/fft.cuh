@@ -1,0 +1,97 @@
+// Warp-level 1024-point complex FFT (the engine's 2048-point real STFT / iSTFT frames are packed into it).
+//
+// N = 32 x 32 Cooley-Tukey: every lane runs a 32-point FFT entirely in registers, the warp transposes once
+// through a padded, warp-private shared-memory tile, and every lane runs a second 32-point FFT.
+//   in : v[r] = x[lane + 32 r]        out : v[r] = X[lane + 32 r]
+// Twiddles come from a device table built once in double precision (no fast-math sincos on the data path).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200x {
+
+constexpr int FFT_N = 1024;            // complex points per frame (real frame length 2048)
+constexpr int FFT_TILE = 32 * 33;      // float2 elements of the per-warp transpose tile
+
+// g_tw2048[j] = (cos(2 pi j / 2048), sin(2 pi j / 2048)); g_hann[n] = periodic Hann(2048);
+// g_wss512[s] = sum_j hann^2[s + 512 j] (steady-state overlap-add envelope for hop 512)
+__device__ float2 g_tw2048[2048];
+__device__ float g_hann[2048];
+__device__ float g_wss512[512];
+
+__device__ __forceinline__ constexpr int brev5(int i) {
+    return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);
+}
+
+// cos / sin of 2 pi q / 32, q = 0..15 (namespace-scope constexpr: folded into immediates after unrolling)
+constexpr float kC32[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                            0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
+                            0.0f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f,
+                            -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
+constexpr float kS32[16] = {0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+                            0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+                            1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
+                            0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
+
+template <bool INV, int K, int J, int M>
+__device__ __forceinline__ void fft32_bfly(float2 (&t)[32]) {
+    constexpr int H = M / 2;
+    constexpr int Q = J * (32 / M);
+    const float2 x = t[K + J + H];
+    float2 wx;
+    if constexpr (Q == 0) {
+        wx = x;
+    } else if constexpr (Q == 8) {
+        wx = INV ? make_float2(-x.y, x.x) : make_float2(x.y, -x.x);
+    } else {
+        constexpr float wr = kC32[Q];
+        constexpr float wi = INV ? kS32[Q] : -kS32[Q];
+        wx = make_float2(x.x * wr - x.y * wi, x.x * wi + x.y * wr);
+    }
+    const float2 u = t[K + J];
+    t[K + J] = make_float2(u.x + wx.x, u.y + wx.y);
+    t[K + J + H] = make_float2(u.x - wx.x, u.y - wx.y);
+}
+
+template <bool INV, int M, int I>
+__device__ __forceinline__ void fft32_stage(float2 (&t)[32]) {
+    // butterfly I of 16 in the stage with span M: group K = (I / (M/2)) * M, offset J = I % (M/2)
+    if constexpr (I < 16) {
+        fft32_bfly<INV, (I / (M / 2)) * M, I % (M / 2), M>(t);
+        fft32_stage<INV, M, I + 1>(t);
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+    float2 t[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[i] = v[brev5(i)];
+    fft32_stage<INV, 2, 0>(t);
+    fft32_stage<INV, 4, 0>(t);
+    fft32_stage<INV, 8, 0>(t);
+    fft32_stage<INV, 16, 0>(t);
+    fft32_stage<INV, 32, 0>(t);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = t[i];
+}
+
+template <bool INV>
+__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* tile, int lane) {
+    fft32<INV>(v);                                     // over n2 (lane = n1): v[k2]
+#pragma unroll
+    for (int k2 = 1; k2 < 32; ++k2) {                  // times W_1024^(n1 k2)
+        const float2 w = __ldg(&g_tw2048[2 * lane * k2]);
+        const float wi = INV ? w.y : -w.y;
+        const float2 x = v[k2];
+        v[k2] = make_float2(x.x * w.x - x.y * wi, x.x * wi + x.y * w.x);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) tile[k2 * 33 + lane] = v[k2];
+    __syncwarp();
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) v[n1] = tile[lane * 33 + n1];
+    fft32<INV>(v);                                     // over n1 (lane = k2): v[k1] = X[32 k1 + k2]
+}
+
+}  // namespace b200x

@@ -1,0 +1,264 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] . W[N,K]^T  (+ fused epilogue)
+//
+//   warp 0 : TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate in TMEM)
+//   warps 2-5 : epilogue (tcgen05.ld -> registers -> fused bias / GELU / positional-encoding / residual -> global)
+//
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.  Used for every dense
+// contraction of the SpecTTTra forward (tokenizer projections, QKV, attention projection, MLP).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200x {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;      // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+    int M, N, K;
+    void* out;            // bf16 [.., ldc] or fp32 [.., ldc]
+    int ldc;
+    int out_mode;         // B200X_GEMM_OUT_*
+    const float* bias;    // [N] or null
+    int act_gelu;
+    const float* resid;   // fp32 [.., ldc] (OUT_F32_RESID), may alias out
+    const float* pe;      // fp32 [group_in, N] (OUT_F32_TOKEN) or null
+    int group_in, group_out, group_off;   // out_row = (m / group_in) * group_out + group_off + m % group_in
+};
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = GEMM_STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
+    static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+    using L = GemmSmem<BN>;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + GEMM_STAGES;
+    uint64_t* tfull_bar = empty_bar + GEMM_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < GEMM_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);      // frees the smem slot once these MMAs retire
+                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);             // accumulator ready for the epilogue
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter + 32)
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const int m = m_blk * GEMM_BM + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            long long out_row = m;
+            int g_idx = 0;
+            if (p.group_in > 0) {
+                g_idx = m % p.group_in;
+                out_row = static_cast<long long>(m / p.group_in) * p.group_out + p.group_off + g_idx;
+            }
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_row + c, r);
+                tmem_wait_ld();
+                const int n0 = n_blk * BN + c;
+                if (row_ok && n0 < p.N) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + i);
+                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                        }
+                    }
+                    if (p.act_gelu) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+                    }
+                    if (p.out_mode == B200X_GEMM_OUT_BF16) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n0;
+                        uint4 w0, w1;
+                        w0.x = pack_bf16(v[0], v[1]);   w0.y = pack_bf16(v[2], v[3]);
+                        w0.z = pack_bf16(v[4], v[5]);   w0.w = pack_bf16(v[6], v[7]);
+                        w1.x = pack_bf16(v[8], v[9]);   w1.y = pack_bf16(v[10], v[11]);
+                        w1.z = pack_bf16(v[12], v[13]); w1.w = pack_bf16(v[14], v[15]);
+                        reinterpret_cast<uint4*>(o)[0] = w0;
+                        reinterpret_cast<uint4*>(o)[1] = w1;
+                    } else {
+                        float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldc + n0;
+                        if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
+                            const float* rs = p.resid + out_row * p.ldc + n0;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 x = *reinterpret_cast<const float4*>(rs + i);
+                                v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
+                            }
+                        } else if (p.pe != nullptr) {
+                            const float* pe = p.pe + static_cast<long long>(g_idx) * p.N + n0;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 x = *reinterpret_cast<const float4*>(pe + i);
+                                v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+static int g_num_sms = 0;
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using L = GemmSmem<BN>;
+    static bool configured = false;
+    if (!configured) {
+        B200X_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        B200X_CUDA_TRY(cudaGetDevice(&dev));
+        B200X_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles = ceil_div(p.M, GEMM_BM) * ceil_div(p.N, BN);
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    gemm_bf16_tn_kernel<BN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+}  // namespace b200x
+
+using namespace b200x;
+
+extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n,
+                               void* d_out, int ldc, int out_mode, const float* d_bias, int act_gelu,
+                               const float* d_resid, const float* d_pe, int group_in, int group_out, int group_off,
+                               void* stream) {
+    B200X_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    B200X_REQUIRE(N % 16 == 0, "gemm: N=%d must be a multiple of 16", N);
+    B200X_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda=%d / ldw=%d must be multiples of 8 (16-byte rows)", lda, ldw);
+    B200X_REQUIRE(out_mode >= B200X_GEMM_OUT_BF16 && out_mode <= B200X_GEMM_OUT_F32_TOKEN, "gemm: bad out_mode %d", out_mode);
+    B200X_REQUIRE(out_mode != B200X_GEMM_OUT_F32_RESID || d_resid != nullptr, "gemm: residual pointer missing");
+    B200X_REQUIRE(ldc % (out_mode == B200X_GEMM_OUT_BF16 ? 8 : 4) == 0, "gemm: ldc=%d not 16-byte aligned", ldc);
+    CUtensorMap tmA, tmB;
+    const uint64_t da[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t sa[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t ba[2] = {GEMM_BK, GEMM_BM};
+    B200X_TRY(make_tmap_bf16(&tmA, d_a, 2, da, sa, ba));
+    const uint64_t dw[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t sw[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t bw[2] = {GEMM_BK, static_cast<uint32_t>(block_n)};
+    B200X_TRY(make_tmap_bf16(&tmB, d_w, 2, dw, sw, bw));
+    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_resid, d_pe, group_in, group_out, group_off};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (block_n) {
+        case 128: return launch_gemm<128>(tmA, tmB, p, s);
+        case 192: return launch_gemm<192>(tmA, tmB, p, s);
+        case 208: return launch_gemm<208>(tmA, tmB, p, s);
+        case 256: return launch_gemm<256>(tmA, tmB, p, s);
+        default: return set_error(B200X_ERR_INVALID, "gemm: unsupported block_n %d (128/192/208/256)", block_n);
+    }
+}

@@ -1,0 +1,274 @@
+// Row-wise and reduction kernels of the hot path (HBM/L2-bound; warp-shuffle reductions, 16-byte accesses):
+//   * layernorm_kernel ........ LayerNorm over the embedding dim, fp32 in -> bf16 (GEMM operand) or fp32 in place
+//   * head_partial/finish ..... final LayerNorm + token mean + Linear(D,1) + sigmoid -> fake-probability per copy
+//   * saliency_kernel ......... delta-prob -> importance map (gather form of map[f0:f1,t0:t1] += d; count += 1;
+//                               map /= count + 1e-8, src/spectrogram_explainability.py:695-707), float64, window order
+//   * band_map_kernel ......... FBP rows: map[(freqs>=low)&(freqs<=high), :] += delta (src/dsp_band_ops.py:652-653)
+//   * rank_kernel ............. stable ranking of windows by key (Python sorted() semantics incl. ties)
+#include "common.h"
+
+namespace b200x {
+
+// one warp per row; D <= 1024, D % 128 == 0 handled with float4 lanes (D = 384 -> 3 float4 per lane)
+template <int VPL>   // float4 vectors per lane
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int rows, int D, const float* __restrict__ gamma_a,
+                 const float* __restrict__ beta_a, const float* __restrict__ gamma_b, const float* __restrict__ beta_b,
+                 int group, int split, float eps, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    // rows are grouped (group rows per copy); rows with (row % group) >= split use the second parameter set
+    const bool second = group > 0 && (row % group) >= split;
+    const float* gamma = second ? gamma_b : gamma_a;
+    const float* beta = second ? beta_b : beta_a;
+    const float4* src = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        v[i] = src[lane + 32 * i];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / D + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float4 g = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
+        const float4 b = reinterpret_cast<const float4*>(beta)[lane + 32 * i];
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (out_bf16 != nullptr) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+            uint2 w;
+            w.x = *reinterpret_cast<uint32_t*>(&p0);
+            w.y = *reinterpret_cast<uint32_t*>(&p1);
+            reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * D)[lane + 32 * i] = w;
+        } else {
+            reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * D)[lane + 32 * i] = o;
+        }
+    }
+}
+
+// partial[copy][slice] = sum over the slice's tokens of dot(LN(x_token), w)
+template <int VPL>
+__global__ void __launch_bounds__(256)
+head_partial_kernel(const float* __restrict__ x, int tokens, int D, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, int use_norm, const float* __restrict__ w,
+                    float* __restrict__ partial) {
+    __shared__ float s_part[8];
+    const int copy = blockIdx.y, slice = blockIdx.x, n_slices = gridDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (tokens + n_slices - 1) / n_slices;
+    const int t_begin = slice * per, t_end = min(t_begin + per, tokens);
+    float acc = 0.f;
+    for (int t = t_begin + warp; t < t_end; t += 8) {
+        const float4* src = reinterpret_cast<const float4*>(x + (static_cast<long long>(copy) * tokens + t) * D);
+        float4 v[VPL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            v[i] = src[lane + 32 * i];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        float mean = 0.f, rstd = 1.f;
+        if (use_norm) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            mean = s / D;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            rstd = rsqrtf(q / D + eps);
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 ww = reinterpret_cast<const float4*>(w)[lane + 32 * i];
+            float4 o = v[i];
+            if (use_norm) {
+                const float4 g = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
+                const float4 b = reinterpret_cast<const float4*>(beta)[lane + 32 * i];
+                o.x = (o.x - mean) * rstd * g.x + b.x; o.y = (o.y - mean) * rstd * g.y + b.y;
+                o.z = (o.z - mean) * rstd * g.z + b.z; o.w = (o.w - mean) * rstd * g.w + b.w;
+            }
+            dot += (o.x * ww.x + o.y * ww.y) + (o.z * ww.z + o.w * ww.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        acc += dot;
+    }
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_part[i];
+        partial[copy * n_slices + slice] = t;
+    }
+}
+
+__global__ void head_finish_kernel(const float* __restrict__ partial, int n_slices, int tokens, float bias, int copies,
+                                   float* __restrict__ logit, float* __restrict__ prob) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= copies) return;
+    float s = 0.f;
+    for (int i = 0; i < n_slices; ++i) s += partial[c * n_slices + i];
+    const float z = s / tokens + bias;
+    if (logit != nullptr) logit[c] = z;
+    prob[c] = 1.0f / (1.0f + expf(-z));
+}
+
+// importance map, gather form.  Each CTA owns a 16 x 128 (freq x time) tile, compacts the windows that touch it into
+// shared memory (window order preserved) and every cell adds its covering windows' deltas in that order in float64.
+__global__ void __launch_bounds__(256)
+saliency_kernel(const int* __restrict__ windows, const double* __restrict__ delta, int n_windows, int n_freq, int n_time,
+                double* __restrict__ map) {
+    extern __shared__ int s_idx[];
+    __shared__ int s_n;
+    const int t_lo = blockIdx.x * 128, f_lo = blockIdx.y * 16;
+    const int t_hi = min(t_lo + 128, n_time), f_hi = min(f_lo + 16, n_freq);
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int i = 0; i < n_windows; ++i) {
+            const int4 w = *reinterpret_cast<const int4*>(windows + 4 * i);
+            if (w.x < t_hi && w.y > t_lo && w.z < f_hi && w.w > f_lo) s_idx[n++] = i;
+        }
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int cell = threadIdx.x; cell < 16 * 128; cell += blockDim.x) {
+        const int f = f_lo + cell / 128, t = t_lo + cell % 128;
+        if (f >= n_freq || t >= n_time) continue;
+        double acc = 0.0, cnt = 0.0;
+        for (int j = 0; j < n; ++j) {
+            const int i = s_idx[j];
+            const int4 w = *reinterpret_cast<const int4*>(windows + 4 * i);
+            if (t >= w.x && t < w.y && f >= w.z && f < w.w) { acc += delta[i]; cnt += 1.0; }
+        }
+        map[static_cast<long long>(f) * n_time + t] = acc / (cnt + 1e-8);
+    }
+}
+
+__global__ void band_map_kernel(const int* __restrict__ rows, const double* __restrict__ delta, int n_bands, int n_freq,
+                                int n_time, double* __restrict__ map) {
+    const int f = blockIdx.y;
+    double acc = 0.0;
+    for (int b = 0; b < n_bands; ++b)
+        if (f >= rows[2 * b] && f < rows[2 * b + 1]) acc += delta[b];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_time; t += gridDim.x * blockDim.x)
+        map[static_cast<long long>(f) * n_time + t] = acc;
+}
+
+// order[rank] = index; rank_i = #{j : key_j before key_i} with ties broken by original index (stable).
+// mode 0: |v| descending, 1: |v| ascending, 2: v descending, 3: v ascending
+__global__ void rank_kernel(const double* __restrict__ v, int n, int mode, int* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool use_abs = mode < 2, desc = (mode == 0 || mode == 2);
+    const double ki = use_abs ? fabs(v[i]) : v[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+        const double kj = use_abs ? fabs(v[j]) : v[j];
+        const bool before = desc ? (kj > ki) : (kj < ki);
+        rank += (before || (kj == ki && j < i)) ? 1 : 0;
+    }
+    order[rank] = i;
+}
+
+__global__ void delta_kernel(const float* __restrict__ prob, float baseline, int n, double* __restrict__ delta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) delta[i] = static_cast<double>(baseline) - static_cast<double>(prob[i]);
+}
+
+}  // namespace b200x
+
+using namespace b200x;
+
+extern "C" int b200x_layernorm(const float* d_x, int rows, int dim, const float* d_gamma, const float* d_beta,
+                               const float* d_gamma2, const float* d_beta2, int group, int split, float eps,
+                               void* d_out_bf16, float* d_out_f32, void* stream) {
+    B200X_REQUIRE(rows > 0 && dim % 128 == 0 && dim <= 1024, "layernorm: dim=%d must be a multiple of 128 (<= 1024)", dim);
+    B200X_REQUIRE((d_out_bf16 != nullptr) != (d_out_f32 != nullptr), "layernorm: exactly one output");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = ceil_div(rows, 8);
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(d_out_bf16);
+#define LN_CASE(V) case V: layernorm_kernel<V><<<grid, 256, 0, s>>>(d_x, rows, dim, d_gamma, d_beta, d_gamma2 ? d_gamma2 : d_gamma, d_beta2 ? d_beta2 : d_beta, group, split, eps, ob, d_out_f32); break;
+    switch (dim / 128) { LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
+        default: return set_error(B200X_ERR_INVALID, "layernorm: dim=%d not instantiated", dim); }
+#undef LN_CASE
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_head(const float* d_x, int copies, int tokens, int dim, const float* d_gamma, const float* d_beta,
+                          float eps, int use_norm, const float* d_w, float bias, float* d_partial, float* d_logit,
+                          float* d_prob, void* stream) {
+    B200X_REQUIRE(copies > 0 && tokens > 0 && dim % 128 == 0 && dim <= 1024, "head: bad sizes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n_slices = 8;
+    dim3 grid(n_slices, copies);
+#define HD_CASE(V) case V: head_partial_kernel<V><<<grid, 256, 0, s>>>(d_x, tokens, dim, d_gamma, d_beta, eps, use_norm, d_w, d_partial); break;
+    switch (dim / 128) { HD_CASE(1) HD_CASE(2) HD_CASE(3) HD_CASE(4) HD_CASE(6) HD_CASE(8)
+        default: return set_error(B200X_ERR_INVALID, "head: dim=%d not instantiated", dim); }
+#undef HD_CASE
+    B200X_CUDA_TRY(cudaGetLastError());
+    head_finish_kernel<<<ceil_div(copies, 128), 128, 0, s>>>(d_partial, n_slices, tokens, bias, copies, d_logit, d_prob);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_head_slices(void) { return 8; }
+
+extern "C" int b200x_delta(const float* d_prob, float baseline, int n, double* d_delta, void* stream) {
+    if (n <= 0) return B200X_OK;
+    delta_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_prob, baseline, n, d_delta);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_saliency_reduce(const int32_t* d_windows, const double* d_delta, int n_windows, int n_freq,
+                                     int n_time, double* d_map, void* stream) {
+    B200X_REQUIRE(n_freq > 0 && n_time > 0 && n_windows >= 0, "saliency: bad sizes");
+    B200X_REQUIRE(n_windows <= 12000, "saliency: too many windows (%d) for the shared-memory index list", n_windows);
+    dim3 grid(ceil_div(n_time, 128), ceil_div(n_freq, 16));
+    const size_t smem = static_cast<size_t>(n_windows > 0 ? n_windows : 1) * sizeof(int);
+    saliency_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(d_windows, d_delta, n_windows, n_freq, n_time, d_map);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_band_map(const int32_t* d_band_rows, const double* d_delta, int n_bands, int n_freq, int n_time,
+                              double* d_map, void* stream) {
+    B200X_REQUIRE(n_freq > 0 && n_time > 0 && n_bands >= 0, "band_map: bad sizes");
+    dim3 grid(ceil_div(n_time, 1024), n_freq);
+    band_map_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_band_rows, d_delta, n_bands, n_freq, n_time, d_map);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_rank(const double* d_values, int n, int mode, int32_t* d_order, void* stream) {
+    B200X_REQUIRE(mode >= 0 && mode <= 3, "rank: bad mode %d", mode);
+    if (n <= 0) return B200X_OK;
+    rank_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(d_values, n, mode, d_order);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}

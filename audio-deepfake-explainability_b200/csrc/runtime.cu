@@ -1,0 +1,70 @@
+// Library-wide runtime pieces of the C-ABI: last-error string, version, tensor-map creation.
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "common.h"
+
+namespace b200x {
+
+static thread_local char g_err[1024] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// cuTensorMapEncodeTiled is resolved through the runtime's driver entry point so that the shared library has
+// no link-time dependency on libcuda.so (it must load, for the symbol check, on a box without a driver).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    });
+    if (g_encode == nullptr) return set_error(B200X_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(B200X_ERR_INVALID, "tensor map base not 16-byte aligned");
+    cuuint64_t gdim[3];
+    cuuint64_t gstr[2];
+    cuuint32_t bdim[3], estr[3];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) {
+            if (strides_bytes[i - 1] % 16 != 0) return set_error(B200X_ERR_INVALID, "tensor map stride %d not 16-byte aligned", i);
+            gstr[i - 1] = strides_bytes[i - 1];
+        }
+    }
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                          gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(B200X_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return B200X_OK;
+}
+
+}  // namespace b200x
+
+extern "C" const char* b200x_last_error(void) { return b200x::g_err; }
+extern "C" int b200x_version(void) { return 100; }
+extern "C" int b200x_set_device(int device) {
+    B200X_CUDA_TRY(cudaSetDevice(device));
+    return B200X_OK;
+}
+extern "C" int b200x_device_count(int* count) {
+    B200X_REQUIRE(count != nullptr, "device_count: NULL output");
+    B200X_CUDA_TRY(cudaGetDeviceCount(count));
+    return B200X_OK;
+}

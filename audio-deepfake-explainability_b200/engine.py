@@ -1,0 +1,186 @@
+"""Python handle on the native engine (``b200x_engine_*`` in include/b200xai.h).
+
+Thin: numpy host buffers in, numpy out; all arithmetic happens in libb200xai.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .weights import ALPHA_120S, SpecTTTraConfig, random_state_dict
+
+RANK_ABS_DESC, RANK_ABS_ASC, RANK_DESC, RANK_ASC = 0, 1, 2, 3
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _c_config(cfg: SpecTTTraConfig) -> _lib.ModelConfig:
+    return _lib.ModelConfig(
+        sample_rate=cfg.sample_rate, n_fft=cfg.n_fft, hop_length=cfg.hop_length, n_mels=cfg.n_mels,
+        f_min=cfg.f_min, f_max=cfg.f_max, top_db=cfg.top_db, amin=cfg.amin, norm_eps=cfg.norm_eps,
+        std_unbiased=int(cfg.std_unbiased), input_spec_dim=cfg.input_spec_dim, input_temp_dim=cfg.input_temp_dim,
+        t_clip=cfg.t_clip, f_clip=cfg.f_clip, embed_dim=cfg.embed_dim, num_heads=cfg.num_heads,
+        num_layers=cfg.num_layers, mlp_hidden=cfg.mlp_hidden, pre_norm=int(cfg.pre_norm),
+        pe_learnable=int(cfg.pe_learnable), qkv_bias=int(cfg.qkv_bias), final_norm=int(cfg.final_norm),
+        tokenizer_ln_eps=cfg.tokenizer_ln_eps, block_ln_eps=cfg.block_ln_eps,
+    )
+
+
+class Engine:
+    """One engine per GPU / process.  ``state_dict``: sonics-named float32 arrays (see weights.py)."""
+
+    def __init__(self, cfg: SpecTTTraConfig = ALPHA_120S, state_dict: Optional[Dict[str, np.ndarray]] = None,
+                 copies_per_chunk: int = 16, max_samples: int = 120 * 16000, device: int = 0):
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = device
+        self.copies_per_chunk = copies_per_chunk
+        self.max_samples = int(max_samples)
+        _lib.check(self.lib.b200x_set_device(device), "set_device")
+        h = C.c_void_p()
+        cc = _c_config(cfg)
+        _lib.check(self.lib.b200x_engine_create(C.byref(cc), copies_per_chunk, self.max_samples, C.byref(h)), "engine_create")
+        self._h = h
+        self.n_samples = 0
+        self.load_state_dict(state_dict if state_dict is not None else random_state_dict(cfg, 0))
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: Dict[str, np.ndarray]) -> None:
+        for name, v in sd.items():
+            if name.startswith("ft_extractor."):
+                continue                       # the mel front-end has no learned parameters
+            a = np.ascontiguousarray(np.asarray(v, dtype=np.float32))
+            _lib.check(self.lib.b200x_engine_set_param(self._h, name.encode(), _ptr(a), a.size), f"set_param({name})")
+        _lib.check(self.lib.b200x_engine_finalize(self._h), "finalize")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.b200x_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ classifier
+    def predict(self, waves: np.ndarray, return_logits: bool = False):
+        """Fake-probability of each equal-length wave (``[L]`` or ``[count, L]``, float32 after ``.float()``)."""
+        w = np.ascontiguousarray(np.asarray(waves, dtype=np.float32))
+        single = w.ndim == 1
+        if single:
+            w = w[None]
+        prob = np.empty(w.shape[0], np.float32)
+        logit = np.empty(w.shape[0], np.float32)
+        _lib.check(self.lib.b200x_engine_predict(self._h, _ptr(w), w.shape[1], w.shape[0], 0, _ptr(prob), _ptr(logit)), "predict")
+        if return_logits:
+            return (prob[0], logit[0]) if single else (prob, logit)
+        return prob[0] if single else prob
+
+    # ------------------------------------------------------------------ track state
+    def set_track(self, wave: np.ndarray) -> None:
+        w = np.ascontiguousarray(np.asarray(wave, dtype=np.float32))
+        _lib.check(self.lib.b200x_engine_set_track(self._h, _ptr(w), w.shape[0], 0), "set_track")
+        self.n_samples = int(w.shape[0])
+
+    def track_shape(self):
+        f, t = C.c_int32(), C.c_int32()
+        _lib.check(self.lib.b200x_engine_track_shape(self._h, C.byref(f), C.byref(t)), "track_shape")
+        return int(f.value), int(t.value)
+
+    def spectrogram(self) -> np.ndarray:
+        f, t = self.track_shape()
+        out = np.empty((f, t), np.complex64)
+        _lib.check(self.lib.b200x_engine_get_spectrogram(self._h, _ptr(out)), "get_spectrogram")
+        return out
+
+    # ------------------------------------------------------------------ sweeps
+    def occlusion_sweep(self, windows: np.ndarray, occlusion_value: float = 0.0) -> np.ndarray:
+        w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
+        prob = np.empty(w.shape[0], np.float32)
+        _lib.check(self.lib.b200x_engine_occlusion_sweep(self._h, _ptr(w), w.shape[0], float(occlusion_value), 0, _ptr(prob)),
+                   "occlusion_sweep")
+        return prob
+
+    def fbp_sweep(self, gains: np.ndarray, normalize_loudness: bool) -> np.ndarray:
+        g = np.ascontiguousarray(np.asarray(gains, dtype=np.float32))
+        n_freq, _ = self.track_shape()
+        if g.ndim != 2 or g.shape[1] != n_freq:
+            raise ValueError(f"gains must be [n_bands, {n_freq}], got {g.shape}")
+        prob = np.empty(g.shape[0], np.float32)
+        _lib.check(self.lib.b200x_engine_fbp_sweep(self._h, _ptr(g), g.shape[0], int(bool(normalize_loudness)), 0, _ptr(prob)),
+                   "fbp_sweep")
+        return prob
+
+    def stem_sweep(self, stems: np.ndarray, masks: np.ndarray) -> np.ndarray:
+        s = np.ascontiguousarray(np.asarray(stems, dtype=np.float32))
+        m = np.ascontiguousarray(np.asarray(masks) != 0).astype(np.uint8)
+        if s.ndim != 2 or m.ndim != 2 or m.shape[1] != s.shape[0]:
+            raise ValueError(f"stems [n_stems, L] / masks [n, n_stems] expected, got {s.shape} / {m.shape}")
+        prob = np.empty(m.shape[0], np.float32)
+        _lib.check(self.lib.b200x_engine_stem_sweep(self._h, _ptr(s), s.shape[0], s.shape[1], _ptr(m), m.shape[0], 0, _ptr(prob)),
+                   "stem_sweep")
+        return prob
+
+    def window_audio(self, windows: np.ndarray) -> np.ndarray:
+        w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
+        _, t = self.track_shape()
+        out = np.empty((w.shape[0], self.cfg.hop_length * (t - 1)), np.float32)
+        _lib.check(self.lib.b200x_engine_window_audio(self._h, _ptr(w), w.shape[0], _ptr(out)), "window_audio")
+        return out
+
+    def band_audio(self, gains: np.ndarray) -> np.ndarray:
+        g = np.ascontiguousarray(np.asarray(gains, dtype=np.float32))
+        _, t = self.track_shape()
+        out = np.empty((g.shape[0], self.cfg.hop_length * (t - 1)), np.float32)
+        _lib.check(self.lib.b200x_engine_band_audio(self._h, _ptr(g), g.shape[0], _ptr(out)), "band_audio")
+        return out
+
+    # ------------------------------------------------------------------ reductions
+    def saliency_map(self, windows: np.ndarray, delta: np.ndarray) -> np.ndarray:
+        w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
+        d = np.ascontiguousarray(np.asarray(delta, dtype=np.float64))
+        f, t = self.track_shape()
+        out = np.empty((f, t), np.float64)
+        _lib.check(self.lib.b200x_engine_saliency_map(self._h, _ptr(w), _ptr(d), w.shape[0], _ptr(out)), "saliency_map")
+        return out
+
+    def band_map(self, band_rows: np.ndarray, delta: np.ndarray) -> np.ndarray:
+        r = np.ascontiguousarray(np.asarray(band_rows, dtype=np.int32)).reshape(-1, 2)
+        d = np.ascontiguousarray(np.asarray(delta, dtype=np.float64))
+        f, t = self.track_shape()
+        out = np.empty((f, t), np.float64)
+        _lib.check(self.lib.b200x_engine_band_map(self._h, _ptr(r), _ptr(d), r.shape[0], _ptr(out)), "band_map")
+        return out
+
+    def rank(self, values: np.ndarray, mode: int) -> np.ndarray:
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.float64))
+        out = np.empty(v.shape[0], np.int32)
+        _lib.check(self.lib.b200x_engine_rank(self._h, _ptr(v), v.shape[0], mode, _ptr(out)), "rank")
+        return out
+
+    # ------------------------------------------------------------------ introspection
+    def debug_buffer(self, name: str):
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.b200x_engine_debug_buffer(self._h, name.encode(), C.byref(p), C.byref(n)), "debug_buffer")
+        return p.value, int(n.value)
+
+    def set_trace(self, device_ptr: Optional[int]) -> None:
+        _lib.check(self.lib.b200x_engine_set_trace(self._h, C.c_void_p(device_ptr or 0)), "set_trace")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b200x_engine_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.b200x_engine_stream(self._h) or 0)
+
+    def synchronize(self) -> None:
+        _lib.check(self.lib.b200x_engine_synchronize(self._h), "synchronize")

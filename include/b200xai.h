@@ -1,0 +1,189 @@
+/* b200xai.h - C ABI of the B200-native perturbation-explainability engine (libb200xai.so).
+ *
+ * Drop-in boundary for the hot path of Michal2711/Audio-Deepfake-Explainability.  The reference has no FFI of
+ * its own (it is pure Python); the "plugin interface" it exposes for this path is the duck-typed predictor
+ *      predict(wave: np.ndarray, sr: int) -> float                       (src/sonics_api.py:259-271)
+ * and the two serial loops that call it once per perturbed copy
+ *      SpectrogramExplainability._compute_occlusion_map                  (src/spectrogram_explainability.py:589-720)
+ *      FrequencyBandPerturbation._compute_component_importance           (src/dsp_band_ops.py:529-666)
+ *      predict_fn_unified (AudioLIME stem recombinations)                (src/lime_explainer.py:283-301)
+ * Each engine-level entry point below replaces one of those call sites with a batched device sweep; the
+ * kernel-level entry points expose every CUDA kernel separately so parity tests can check each stage.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns B200X_OK (0) or an error code and
+ * b200x_last_error() holds the message (thread-local).  There is NO CPU fallback and no silent 0.0 result
+ * (contrast src/spectrogram_explainability.py:357-362): a failure is always reported.
+ * Pointers prefixed d_ are device pointers; "stream" is a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef B200XAI_H
+#define B200XAI_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200X_OK 0
+#define B200X_ERR_INVALID 1
+#define B200X_ERR_CUDA 2
+#define B200X_ERR_STATE 3
+
+#define B200X_GEMM_OUT_BF16 0      /* out = bf16(act(acc + bias))                                   */
+#define B200X_GEMM_OUT_F32_RESID 1 /* out = resid + acc + bias              (fp32, in place allowed) */
+#define B200X_GEMM_OUT_F32_TOKEN 2 /* out = act(acc + bias) + pe[row % group_in]  (fp32, row remap)  */
+
+#define B200X_MASK_NONE 0
+#define B200X_MASK_OCCLUDE 1   /* S[f0:f1, t0:t1] = value          (spectrogram_explainability.py:670-671) */
+#define B200X_MASK_BAND_GAIN 2 /* S *= gain[f]                     (dsp_band_ops.py:576-579)               */
+#define B200X_MASK_KEEP_ONLY 3 /* zeros except S[f0:f1, t0:t1]     (spectrogram_explainability.py:472-475) */
+
+const char* b200x_last_error(void);
+int b200x_version(void);
+/* select the CUDA device used by subsequent calls from this thread (one process per GPU: pass LOCAL_RANK) */
+int b200x_set_device(int device);
+int b200x_device_count(int* count);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Kernel-level entry points (device pointers)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* librosa.stft(y, 2048, 512, 2048, 'hann', center=True) [reflect_pad = 0: zero padding] or the classifier's
+ * torch.stft framing [reflect_pad = 1].  d_spec: complex64 interleaved, frame-major [1 + n/hop][spec_stride].
+ * replaces: librosa.stft call, src/spectrogram_explainability.py:379-386, src/dsp_band_ops.py:394-401 */
+int b200x_stft(const float* d_wave, int64_t n_samples, int n_fft, int hop, int reflect_pad, void* d_spec,
+               int spec_stride, void* stream);
+
+/* Batched librosa.istft of `copies` perturbed versions of one spectrogram; the perturbation is applied in the
+ * load stage (mode = B200X_MASK_*), d_windows int32 [copies][4] = t0,t1,f0,f1, d_gains float [copies][1025].
+ * Writes hop*(n_frames-1) samples per copy at d_y + copy*y_stride; d_sumsq (optional, pre-zeroed double[copies])
+ * receives sum(y^2) for match_rms.  replaces: src/spectrogram_explainability.py:670-680, dsp_band_ops.py:578-580 */
+int b200x_istft_masked(const void* d_spec, int spec_stride, int n_frames, int copies, int mode,
+                       const int32_t* d_windows, float occlusion_value, const float* d_gains, float* d_y,
+                       int64_t y_stride, double* d_sumsq, void* stream);
+
+/* Classifier front-end (sonics FeatureExtractor = torchaudio MelSpectrogram + AmplitudeToDB, third-party):
+ * reflect-padded STFT -> power -> HTK mel -> 10 log10(max(., amin)).  d_db float [copies][n_frames][n_mels];
+ * d_cta_max float [copies][ceil(n_frames / b200x_mel_frames_per_cta())].  If d_sumsq != NULL the samples are
+ * scaled by ref_rms / sqrt(sumsq/rms_count + 1e-8) first (match_rms, src/dsp_band_ops.py:228-233). */
+int b200x_mel_frames_per_cta(void);
+int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_samples, int copies, int sample_rate, int n_mels,
+                 double f_min, double f_max, double amin, const double* d_sumsq, double ref_rms, int64_t rms_count,
+                 float* d_db, float* d_cta_max, void* stream);
+
+/* top_db clamp, (x-mean)/(std+eps), F.interpolate(bilinear) along time to out_t, bf16, in both tokenizer operand
+ * layouts: d_img_t [copies][out_t][n_mels], d_img_f [copies][n_mels][ld_f].  d_partial: 32*copies double2 scratch. */
+int b200x_mel_normalize_resize(const float* d_db, const float* d_cta_max, int n_cta_max, int copies, int n_frames,
+                               int n_mels, float top_db, int unbiased, float eps, int out_t, void* d_partial,
+                               float* d_floor, void* d_img_t, void* d_img_f, int ld_f, void* stream);
+
+/* y[b] = sum_i masks[b][i] * stems[i]   (src/lime_explainer.py:283-301 composition) */
+int b200x_mix_stems(const float* d_stems, int64_t n_samples, int n_stems, const uint8_t* d_masks, int copies,
+                    float* d_y, int64_t y_stride, void* stream);
+
+/* tcgen05 GEMM  C[M,N] = A[M,K] . W[N,K]^T, bf16 operands (row-major, K contiguous), fp32 accumulation in TMEM,
+ * fused epilogue per B200X_GEMM_OUT_*.  block_n in {128,192,208,256}.  Replaces every nn.Linear / Conv1d
+ * contraction of the third-party SpecTTTra forward. */
+int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n, void* d_out,
+                    int ldc, int out_mode, const float* d_bias, int act_gelu, const float* d_resid, const float* d_pe,
+                    int group_in, int group_out, int group_off, void* stream);
+
+/* fused softmax(Q K^T / sqrt(d)) V for d_qkv bf16 [copies*tokens][3*heads*64] = [q|k|v]; d_out bf16
+ * [copies*tokens][heads*64].  (F.scaled_dot_product_attention inside the third-party encoder) */
+int b200x_attention(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int head_dim, void* stream);
+
+/* LayerNorm over dim (fp32 in); rows with (row % group) >= split use (gamma2, beta2) when group > 0.
+ * Exactly one of d_out_bf16 / d_out_f32 (may alias d_x) is non-NULL. */
+int b200x_layernorm(const float* d_x, int rows, int dim, const float* d_gamma, const float* d_beta,
+                    const float* d_gamma2, const float* d_beta2, int group, int split, float eps, void* d_out_bf16,
+                    float* d_out_f32, void* stream);
+
+/* final LayerNorm (optional) + token mean + Linear(dim,1) + sigmoid.  d_partial: copies*b200x_head_slices() floats. */
+int b200x_head_slices(void);
+int b200x_head(const float* d_x, int copies, int tokens, int dim, const float* d_gamma, const float* d_beta, float eps,
+               int use_norm, const float* d_w, float bias, float* d_partial, float* d_logit, float* d_prob,
+               void* stream);
+
+/* delta[i] = (double)baseline - (double)prob[i]      (importance = baseline_pred - occluded_pred, :684) */
+int b200x_delta(const float* d_prob, float baseline, int n, double* d_delta, void* stream);
+
+/* importance map: map[f0:f1,t0:t1] += delta; count += 1; map /= count + 1e-8  (float64 [n_freq][n_time], window order;
+ * src/spectrogram_explainability.py:695-696, 707) */
+int b200x_saliency_reduce(const int32_t* d_windows, const double* d_delta, int n_windows, int n_freq, int n_time,
+                          double* d_map, void* stream);
+
+/* FBP rows: map[rows[b][0]:rows[b][1], :] += delta[b]  (src/dsp_band_ops.py:652-653) */
+int b200x_band_map(const int32_t* d_band_rows, const double* d_delta, int n_bands, int n_freq, int n_time,
+                   double* d_map, void* stream);
+
+/* stable ordering (Python sorted() semantics): mode 0 |v| desc, 1 |v| asc, 2 v desc, 3 v asc
+ * (src/spectrogram_explainability.py:428-434, 566-571) */
+int b200x_rank(const double* d_values, int n, int mode, int32_t* d_order, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Engine-level entry points (host or device buffers; one engine per GPU / process; not re-entrant per engine)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b200x_engine b200x_engine;
+
+typedef struct b200x_model_config {
+    int32_t sample_rate, n_fft, hop_length, n_mels;
+    double f_min, f_max, top_db, amin;
+    float norm_eps;
+    int32_t std_unbiased;
+    int32_t input_spec_dim, input_temp_dim, t_clip, f_clip;
+    int32_t embed_dim, num_heads, num_layers, mlp_hidden;
+    int32_t pre_norm, pe_learnable, qkv_bias, final_norm;
+    float tokenizer_ln_eps, block_ln_eps;
+} b200x_model_config;
+
+/* copies_per_chunk: perturbed copies processed per pass (activation working set sized to stay L2-resident). */
+int b200x_engine_create(const b200x_model_config* cfg, int copies_per_chunk, int64_t max_samples, b200x_engine** out);
+void b200x_engine_destroy(b200x_engine* e);
+
+/* sonics state-dict entry by name (float32 host data), then finalize (packs bf16 operands; all names required). */
+int b200x_engine_set_param(b200x_engine* e, const char* name, const float* data, int64_t numel);
+int b200x_engine_finalize(b200x_engine* e);
+
+/* LocalSonnics.predict for `count` equal-length waves: fake-probability per wave (src/sonics_api.py:259-271). */
+int b200x_engine_predict(b200x_engine* e, const float* waves, int64_t n_samples, int count, int on_device, float* prob,
+                         float* logit /* nullable */);
+
+/* Load one track: uploads the wave, computes the explainer STFT (librosa semantics) and keeps both resident. */
+int b200x_engine_set_track(b200x_engine* e, const float* wave, int64_t n_samples, int on_device);
+int b200x_engine_track_shape(b200x_engine* e, int32_t* n_freq, int32_t* n_time);
+/* complex64 [n_freq][n_time] interleaved, the layout of librosa.stft / OcclusionResult.S */
+int b200x_engine_get_spectrogram(b200x_engine* e, float* spec_host);
+
+/* The occlusion hot loop (src/spectrogram_explainability.py:665-703) for `n` windows (int32 [n][4] = t0,t1,f0,f1):
+ * prob[i] = predict(istft(S with window i set to occlusion_value)).  Buffers are host (on_device=0) or device. */
+int b200x_engine_occlusion_sweep(b200x_engine* e, const int32_t* windows, int n, float occlusion_value, int on_device,
+                                 float* prob);
+/* The FBP hot loop (src/dsp_band_ops.py:573-586) for `n` band gains (float [n][n_freq] = keep + att*(1-keep)). */
+int b200x_engine_fbp_sweep(b200x_engine* e, const float* gains, int n, int normalize_loudness, int on_device,
+                           float* prob);
+/* AudioLIME recombinations (src/lime_explainer.py:283-301): stems float [n_stems][n_samples], masks uint8 [n][n_stems]. */
+int b200x_engine_stem_sweep(b200x_engine* e, const float* stems, int n_stems, int64_t n_samples, const uint8_t* masks,
+                            int n, int on_device, float* prob);
+/* Top-window audio reconstructed from the patch alone (src/spectrogram_explainability.py:472-483):
+ * audio float [n][hop*(n_time-1)] host. */
+int b200x_engine_window_audio(b200x_engine* e, const int32_t* windows, int n, float* audio_host);
+/* Perturbed audio of the FBP bands (for separated_bands WAVs, src/dsp_band_ops.py:608-639): float [n][hop*(n_time-1)]. */
+int b200x_engine_band_audio(b200x_engine* e, const float* gains, int n, float* audio_host);
+
+/* Reductions on host buffers (map is float64 [n_freq][n_time]). */
+int b200x_engine_saliency_map(b200x_engine* e, const int32_t* windows, const double* delta, int n, double* map_host);
+int b200x_engine_band_map(b200x_engine* e, const int32_t* band_rows, const double* delta, int n, double* map_host);
+int b200x_engine_rank(b200x_engine* e, const double* values, int n, int mode, int32_t* order_host);
+
+/* Introspection for tests / profiling: device pointer of a named intermediate of the LAST processed chunk
+ * ("y","db","img_t","img_f","x","h","qkv","att","hid","prob","S"), its byte size; number of kernel launches so far. */
+int b200x_engine_debug_buffer(b200x_engine* e, const char* name, void** d_ptr, int64_t* bytes);
+int b200x_engine_set_trace(b200x_engine* e, float* d_trace /* [layers+1][copies*tokens][dim] or NULL */);
+int64_t b200x_engine_launch_count(b200x_engine* e);
+void* b200x_engine_stream(b200x_engine* e);
+int b200x_engine_synchronize(b200x_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200XAI_H */

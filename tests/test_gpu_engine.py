@@ -1,0 +1,147 @@
+"""Engine-level parity: SpecTTTra forward, occlusion sweep, FBP sweep, stem sweep vs the CPU oracle
+(tolerance from BASELINE.json north_star: 1e-3 absolute on per-window delta-prob and saliency values; window /
+band indexing and the top-k set bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from audio_deepfake_explainability_b200 import grid, synth
+from audio_deepfake_explainability_b200.engine import Engine
+from audio_deepfake_explainability_b200.weights import ALPHA_120S, random_state_dict
+from oracle import dsp, loops, spectttra
+
+pytestmark = pytest.mark.gpu
+CFG = ALPHA_120S
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return random_state_dict(CFG, 0)
+
+
+@pytest.fixture(scope="module")
+def eng(sd):
+    e = Engine(CFG, sd, copies_per_chunk=4, max_samples=30 * 16000)
+    yield e
+    e.close()
+
+
+def test_forward_stages_match_oracle(eng, sd):
+    y = synth.synth_track("REAL", 0, 16000, 20.0)
+    M = CFG.num_tokens
+    trace = torch.zeros(CFG.num_layers + 1, M, CFG.embed_dim, device="cuda")
+    eng.set_trace(trace.data_ptr())
+    try:
+        prob, logit = eng.predict(y, return_logits=True)
+    finally:
+        eng.set_trace(None)
+    t = torch.from_numpy(y).unsqueeze(0)
+    img = spectttra.resize(dsp.mel_frontend(t, CFG), CFG)
+    for mode, tol_tok, tol_layer, tol_logit in (("bf16", 2e-3, 3e-2, 3e-3), ("fp32", 3e-2, 1e-1, 1.5e-2)):
+        tok = spectttra.tokenize(img, sd, CFG, mode)
+        _, layers = spectttra.encoder(tok, sd, CFG, mode, return_all=True)
+        e0 = (trace[0].cpu() - tok[0]).abs().max().item()
+        assert e0 < tol_tok, f"{mode}: tokenizer max err {e0}"
+        for l, ref in enumerate(layers):
+            el = (trace[l + 1].cpu() - ref[0]).abs().max().item()
+            assert el < tol_layer * max(1.0, ref.abs().max().item() / 4), f"{mode}: layer {l} max err {el}"
+        ref_logit = spectttra.forward_logits(t, sd, CFG, mode).item()
+        assert abs(float(logit) - ref_logit) < tol_logit, f"{mode}: logit {float(logit)} vs {ref_logit}"
+        assert abs(float(prob) - 1.0 / (1.0 + np.exp(-ref_logit))) < TOL
+
+
+def test_predict_batch_equals_single(eng):
+    ys = np.stack([synth.synth_track(f, 1, 16000, 6.0) for f in ("REAL", "SUNO", "UDIO", "ElevenLabs", "SUNO_PRO")])
+    pb = eng.predict(ys)
+    ps = np.array([eng.predict(y) for y in ys])
+    assert np.array_equal(pb, ps)                    # batching / chunking must not change a single bit
+    assert len(set(np.round(pb, 6))) > 1
+
+
+def test_occlusion_sweep_matches_oracle(eng, sd):
+    y = synth.synth_track("UDIO", 0, 16000, 24.0)[: 16000 * 24 - 200]      # ragged length: iSTFT shorter than y
+    eng.set_track(y)
+    n_freq, n_time = eng.track_shape()
+    assert (n_freq, n_time) == grid.stft_shape(len(y), 2048, 512)
+    S = eng.spectrogram()
+    S_ref = dsp.stft(y).numpy()
+    assert np.abs(S - S_ref).max() < 2e-5 * np.abs(S_ref).max()
+    wins = grid.occlusion_windows(n_freq, n_time, 256, 256, 20.0, 20.0)
+    sel = np.concatenate([wins[:3], wins[-3:], wins[len(wins) // 2: len(wins) // 2 + 2]])
+    base = float(eng.predict(y))
+    prob = eng.occlusion_sweep(sel, 0.0)
+    delta = np.float64(np.float32(base)) - prob.astype(np.float64)
+    pred32 = spectttra.OraclePredictor(sd, CFG, "fp32")
+    base_ref = pred32.predict(y, 16000)
+    assert abs(base - base_ref) < TOL
+    for i, (t0, t1, f0, f1) in enumerate(sel):
+        S_occ = S_ref.copy()
+        S_occ[f0:f1, t0:t1] = 0.0
+        y_occ = dsp.istft(S_occ).numpy()
+        y_occ = np.pad(y_occ, (0, len(y) - len(y_occ)))
+        d_ref = base_ref - pred32.predict(y_occ, 16000)
+        assert abs(delta[i] - d_ref) < TOL, f"window {i}: {delta[i]} vs {d_ref}"
+    assert np.abs(delta).max() > 1e-4                 # the comparison is not vacuous
+    # reductions through the engine: map identical to the reference loop given the same deltas
+    m = eng.saliency_map(sel, delta)
+    assert np.array_equal(m, loops.saliency_from_windows(sel, delta, n_freq, n_time))
+    for mode, key, desc in ((0, abs, True), (1, abs, False), (2, float, True), (3, float, False)):
+        assert eng.rank(delta, mode).tolist() == sorted(range(len(delta)), key=lambda i: key(delta[i]), reverse=desc)
+    # chunking invariance (copies_per_chunk = 4, 8 windows = 2 chunks) and determinism
+    assert np.array_equal(prob, eng.occlusion_sweep(sel, 0.0))
+    assert np.array_equal(prob[5:6], eng.occlusion_sweep(sel[5:6], 0.0))
+    # top-window audio (keep-only iSTFT)
+    aud = eng.window_audio(sel[:2])
+    for i in range(2):
+        p = dict(t_start=int(sel[i][0]), t_end=int(sel[i][1]), f_start=int(sel[i][2]), f_end=int(sel[i][3]))
+        ref = loops.window_audio(y, S_ref, p, 512, 2048, use_original_audio=False)
+        start = p["t_start"] * 512
+        assert np.abs(aud[i][start:start + len(ref)] - ref).max() < 3e-6
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_fbp_sweep_matches_oracle(eng, sd, normalize):
+    y = synth.synth_track("SUNO", 2, 16000, 16.0)
+    eng.set_track(y)
+    bands = grid.FREQUENCY_BAND_PRESETS["high_resolution"]
+    sel = [bands[i] for i in (0, 3, 6, 8, 12)]         # incl. an empty band above Nyquist
+    gains = grid.band_gain_table(sel, 16000, 2048, 0.25, "rel", 0.2, 5.0, 500.0, 200.0)
+    base = float(eng.predict(y))
+    prob = eng.fbp_sweep(gains, normalize)
+    delta = np.float64(np.float32(base)) - prob.astype(np.float64)
+    ref = loops.fbp_component(y, spectttra.OraclePredictor(sd, CFG, "fp32"), 16000, sel, 0.25, "rel", 200.0, 0.2, 5.0, 500.0,
+                              normalize_loudness=normalize)
+    ref_delta = np.array([b["importance"] for b in ref.batch_importances])
+    assert np.abs(delta - ref_delta).max() < TOL, (delta, ref_delta)
+    assert abs(delta[-1]) < TOL                         # empty band: keep == 1 everywhere
+    rows = grid.band_bin_ranges(sel, 16000, 2048)
+    assert np.array_equal(eng.band_map(rows, ref_delta), ref.importance_map)
+
+
+def test_stem_sweep_matches_oracle(eng, sd):
+    y, stems = synth.synth_track("REAL", 3, 16000, 8.0, with_stems=True)
+    st = np.stack([stems[k] for k in sorted(stems)])
+    masks = np.array([[1, 1, 1, 1], [1, 0, 0, 0], [0, 1, 1, 0], [0, 0, 0, 0]], np.uint8)
+    prob = eng.stem_sweep(st, masks)
+    ref = loops.stem_mask_probs(st, masks, spectttra.OraclePredictor(sd, CFG, "fp32"), 16000)
+    assert np.abs(prob - ref[:, 1]).max() < TOL
+
+
+def test_errors_are_loud(sd):
+    e = Engine(CFG, sd, copies_per_chunk=2, max_samples=8 * 16000)
+    try:
+        with pytest.raises(RuntimeError):
+            e.occlusion_sweep(np.array([[0, 1, 0, 1]], np.int32))            # no track loaded
+        e.set_track(synth.synth_track("REAL", 0, 16000, 4.0))
+        with pytest.raises(RuntimeError):
+            e.occlusion_sweep(np.array([[0, 99999, 0, 1]], np.int32))        # window outside the spectrogram
+        with pytest.raises(RuntimeError):
+            e.predict(np.zeros(16 * 16000, np.float32))                      # longer than max_samples
+        assert e.occlusion_sweep(np.zeros((0, 4), np.int32)).shape == (0,)   # empty sweep is a no-op
+    finally:
+        e.close()
+    bad = dict(sd)
+    bad.pop("classifier.bias")
+    with pytest.raises(RuntimeError):
+        Engine(CFG, bad, copies_per_chunk=2, max_samples=8 * 16000)

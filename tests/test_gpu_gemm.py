@@ -1,0 +1,86 @@
+"""tcgen05 GEMM kernel vs a plain fp32 matmul of the same bf16-rounded operands (through the C ABI)."""
+import pytest
+import torch
+
+from gpu_util import P, bf16_round, lib, ok
+
+pytestmark = pytest.mark.gpu
+OUT_BF16, OUT_RESID, OUT_TOKEN = 0, 1, 2
+
+
+def _run(M, N, K, bn, mode, bias=True, gelu=False, group=None, lda=None, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lda = lda or K
+    a = torch.randn(M, lda, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g) if bias else None
+    ref = a[:, :K].float() @ w.float().T
+    if b is not None:
+        ref = ref + b
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    da, dw = a.cuda(), w.cuda()
+    db = b.cuda() if b is not None else None
+    if mode == OUT_BF16:
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ok(lib().b200x_gemm_bf16(P(da), lda, P(dw), K, M, N, K, bn, P(out), N, mode, P(db), int(gelu), P(None), P(None), 0, 0, 0, P(None)))
+        got = out.float().cpu()
+        tol = 2e-2
+    elif mode == OUT_RESID:
+        res = torch.randn(M, N, generator=g)
+        ref = ref + res
+        out = res.cuda().clone()
+        ok(lib().b200x_gemm_bf16(P(da), lda, P(dw), K, M, N, K, bn, P(out), N, mode, P(db), int(gelu), P(out), P(None), 0, 0, 0, P(None)))
+        got = out.cpu()
+        tol = 2e-4
+    else:
+        gin, gout, goff = group
+        pe = torch.randn(gin, N, generator=g)
+        copies = M // gin
+        out = torch.zeros(copies * gout, N, device="cuda")
+        ok(lib().b200x_gemm_bf16(P(da), lda, P(dw), K, M, N, K, bn, P(out), N, mode, P(db), int(gelu), P(None), P(pe.cuda()), gin, gout, goff, P(None)))
+        full = out.cpu().reshape(copies, gout, N)
+        got = full[:, goff:goff + gin].reshape(M, N)
+        ref = (ref.reshape(copies, gin, N) + pe).reshape(M, N)
+        assert full[:, :goff].abs().max() == 0 if goff else True
+        tol = 2e-4
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * max(scale, 1.0), f"max err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("bn", [128, 192, 208, 256])
+def test_gemm_small_all_tiles(bn):
+    _run(300, 416, 384, bn, OUT_BF16, bias=True, gelu=False)
+
+
+def test_gemm_qkv_shape():
+    _run(2 * 1376, 1152, 384, 192, OUT_BF16, bias=False)
+
+
+def test_gemm_fc1_gelu_padded_hidden():
+    _run(1376 + 77, 1040, 384, 208, OUT_BF16, bias=True, gelu=True)
+
+
+def test_gemm_fc2_residual_k1040():
+    _run(1376 + 77, 384, 1040, 192, OUT_RESID, bias=True)
+
+
+def test_gemm_many_tiles_persistent():
+    _run(148 * 128 * 2 + 50, 384, 384, 192, OUT_RESID, bias=True)   # > 1 tile per CTA, exercises both TMEM stages
+
+
+def test_gemm_token_mode_temporal():
+    _run(2 * 1248, 384, 384, 192, OUT_TOKEN, bias=False, gelu=True, group=(1248, 1376, 0))
+
+
+def test_gemm_token_mode_spectral_k3744():
+    _run(2 * 128, 384, 3744, 192, OUT_TOKEN, bias=False, gelu=True, group=(128, 1376, 1248))
+
+
+def test_gemm_rejects_bad_arguments():
+    a = torch.zeros(128, 384, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError):
+        ok(lib().b200x_gemm_bf16(P(a), 384, P(a), 384, 128, 100, 384, 192, P(a), 100, 0, P(None), 0, P(None), P(None), 0, 0, 0, P(None)))
+    with pytest.raises(RuntimeError):
+        ok(lib().b200x_gemm_bf16(P(a), 384, P(a), 384, 128, 128, 384, 64, P(a), 128, 0, P(None), 0, P(None), P(None), 0, 0, 0, P(None)))
