@@ -66,7 +66,8 @@ SIGNATURES = {
     "b200x_engine_occlusion_sweep": (C.c_int, [VP, VP, C.c_int, C.c_float, C.c_int, VP]),
     "b200x_engine_fbp_sweep": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, VP]),
     "b200x_engine_stem_sweep": (C.c_int, [VP, VP, C.c_int, C.c_int64, VP, C.c_int, C.c_int, VP]),
-    "b200x_engine_window_audio": (C.c_int, [VP, VP, C.c_int, VP]),
+    "b200x_engine_window_audio": (C.c_int, [VP, VP, C.c_int, VP, C.c_int64, VP]),
+    "b200x_engine_occluded_audio": (C.c_int, [VP, VP, C.c_int, C.c_float, VP]),
     "b200x_engine_band_audio": (C.c_int, [VP, VP, C.c_int, VP]),
     "b200x_engine_saliency_map": (C.c_int, [VP, VP, VP, C.c_int, VP]),
     "b200x_engine_band_map": (C.c_int, [VP, VP, VP, C.c_int, VP]),
@@ -74,6 +75,8 @@ SIGNATURES = {
     "b200x_engine_debug_buffer": (C.c_int, [VP, C.c_char_p, C.POINTER(VP), C.POINTER(C.c_int64)]),
     "b200x_engine_set_trace": (C.c_int, [VP, VP]),
     "b200x_engine_launch_count": (C.c_int64, [VP]),
+    "b200x_engine_set_timing": (C.c_int, [VP, C.c_int]),
+    "b200x_engine_get_timing": (C.c_int, [VP, VP, VP]),
     "b200x_engine_stream": (VP, [VP]),
     "b200x_engine_synchronize": (C.c_int, [VP]),
 }

@@ -85,9 +85,37 @@ struct b200x_engine {
     DevBuf windows, gains, masks, stems, delta, order, map;
     int last_copies = 0;
     float* trace = nullptr;
+
+    // optional per-kernel-class CUDA-event timing (bench roofline breakdown)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_class;     // class of the i-th (start, stop) pair
+    size_t ev_used = 0;
 };
 
+enum KernelClass { KC_ISTFT = 0, KC_MEL = 1, KC_RESIZE = 2, KC_GEMM = 3, KC_ATTN = 4, KC_LN = 5, KC_HEAD = 6, KC_OTHER = 7, KC_COUNT = 8 };
+
 namespace {
+
+// RAII-free bracket: records a (start, stop) event pair around a launch when timing is enabled
+struct Timed {
+    b200x_engine* e;
+    size_t slot = 0;
+    bool on = false;
+    Timed(b200x_engine* eng, int cls) : e(eng) {
+        if (!e->timing) return;
+        if (e->ev_used + 2 > e->ev_pool.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev_pool.push_back(ev); }
+        }
+        slot = e->ev_used;
+        e->ev_used += 2;
+        e->ev_class.push_back(cls);
+        cudaEventRecord(e->ev_pool[slot], e->stream);
+        on = true;
+    }
+    ~Timed() { if (on) cudaEventRecord(e->ev_pool[slot + 1], e->stream); }
+};
+#define TIMED(cls, call) do { Timed _t(e, cls); B200X_TRY(call); } while (0)
 
 int upload(DevBuf& b, const void* host, size_t bytes) {
     B200X_TRY(b.alloc(bytes));
@@ -124,22 +152,22 @@ int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* 
     const int n_cta = ceil_div(n_frames, b200x_mel_frames_per_cta());
     const int D = e->D, T = e->T, M = copies * T;
     e->last_copies = copies;
-    B200X_TRY(b200x_mel_db(e->y.as<float>(), e->y_stride, n_samples, copies, c.sample_rate, c.n_mels, c.f_min, c.f_max, c.amin,
+    TIMED(KC_MEL, b200x_mel_db(e->y.as<float>(), e->y_stride, n_samples, copies, c.sample_rate, c.n_mels, c.f_min, c.f_max, c.amin,
                            d_sumsq, e->ref_rms, rms_count, e->db.as<float>(), e->cta_max.as<float>(), s));
-    B200X_TRY(b200x_mel_normalize_resize(e->db.as<float>(), e->cta_max.as<float>(), n_cta, copies, n_frames, c.n_mels,
+    TIMED(KC_RESIZE, b200x_mel_normalize_resize(e->db.as<float>(), e->cta_max.as<float>(), n_cta, copies, n_frames, c.n_mels,
                                          static_cast<float>(c.top_db), c.std_unbiased, c.norm_eps, c.input_temp_dim,
                                          e->partial.p, e->floor_v.as<float>(), e->img_t.p, e->img_f.p, c.input_temp_dim, s));
     e->launches += 3;
     // tokenizers: temporal rows = t_clip consecutive time steps x n_mels; spectral rows = one mel row over time
     const int Kt = c.t_clip * c.input_spec_dim;
-    B200X_TRY(b200x_gemm_bf16(e->img_t.p, Kt, e->tok_t_w.p, Kt, copies * e->Tt, D, Kt, pick_block_n(D), e->x.p, D,
+    TIMED(KC_GEMM, b200x_gemm_bf16(e->img_t.p, Kt, e->tok_t_w.p, Kt, copies * e->Tt, D, Kt, pick_block_n(D), e->x.p, D,
                               B200X_GEMM_OUT_F32_TOKEN, e->tok_t_b.as<float>(), 1, nullptr, e->pe_t.as<float>(), e->Tt, T, 0, s));
-    B200X_TRY(b200x_gemm_bf16(e->img_f.p, c.input_temp_dim, e->tok_s_w.p, c.input_temp_dim, copies * e->Ts, D,
+    TIMED(KC_GEMM, b200x_gemm_bf16(e->img_f.p, c.input_temp_dim, e->tok_s_w.p, c.input_temp_dim, copies * e->Ts, D,
                               c.input_temp_dim, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_TOKEN, e->tok_s_b.as<float>(), 1,
                               nullptr, e->pe_s.as<float>(), e->Ts, T, e->Tt, s));
     e->launches += 2;
     if (c.pre_norm) {
-        B200X_TRY(b200x_layernorm(e->x.as<float>(), M, D, e->np_t_g.as<float>(), e->np_t_b.as<float>(), e->np_s_g.as<float>(),
+        TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, e->np_t_g.as<float>(), e->np_t_b.as<float>(), e->np_s_g.as<float>(),
                                   e->np_s_b.as<float>(), T, e->Tt, c.tokenizer_ln_eps, nullptr, e->x.as<float>(), s));
         e->launches += 1;
     }
@@ -147,26 +175,38 @@ int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* 
     if (e->trace) B200X_CUDA_TRY(cudaMemcpyAsync(e->trace, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
-        B200X_TRY(b200x_layernorm(e->x.as<float>(), M, D, w.n1_g.as<float>(), w.n1_b.as<float>(), nullptr, nullptr, 0, 0,
+        TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n1_g.as<float>(), w.n1_b.as<float>(), nullptr, nullptr, 0, 0,
                                   c.block_ln_eps, e->h.p, nullptr, s));
-        B200X_TRY(b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
+        TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
                                   c.qkv_bias ? w.qkv_b.as<float>() : nullptr, 0, nullptr, nullptr, 0, 0, 0, s));
-        B200X_TRY(b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, s));
-        B200X_TRY(b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
+        TIMED(KC_ATTN, b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, s));
+        TIMED(KC_GEMM, b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
                                   w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
-        B200X_TRY(b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
+        TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
                                   c.block_ln_eps, e->h.p, nullptr, s));
-        B200X_TRY(b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
+        TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
                                   w.fc1_b.as<float>(), 1, nullptr, nullptr, 0, 0, 0, s));
-        B200X_TRY(b200x_gemm_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, pick_block_n(D), e->x.p, D,
+        TIMED(KC_GEMM, b200x_gemm_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, pick_block_n(D), e->x.p, D,
                                   B200X_GEMM_OUT_F32_RESID, w.fc2_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
         e->launches += 7;
         if (e->trace)
             B200X_CUDA_TRY(cudaMemcpyAsync(e->trace + static_cast<size_t>(l + 1) * M * D, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
     }
-    B200X_TRY(b200x_head(e->x.as<float>(), copies, T, D, e->fn_g.as<float>(), e->fn_b.as<float>(), c.block_ln_eps, c.final_norm,
+    TIMED(KC_HEAD, b200x_head(e->x.as<float>(), copies, T, D, e->fn_g.as<float>(), e->fn_b.as<float>(), c.block_ln_eps, c.final_norm,
                          e->cls_w.as<float>(), e->cls_b, e->head_part.as<float>(), d_logit, d_prob, s));
     e->launches += 2;
+    return B200X_OK;
+}
+
+// reference RMS for match_rms: sqrt(mean(sig^2) + 1e-8) in float64 on the host, like the reference (dsp_band_ops.py:228-233)
+int ensure_ref_rms(b200x_engine* e) {
+    if (e->ref_rms >= 0.0) return B200X_OK;
+    std::vector<float> tmp(e->L);
+    B200X_CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->wave.p, e->L * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    double acc = 0.0;
+    for (int64_t i = 0; i < e->L; ++i) { const double v = tmp[i]; acc += v * v; }
+    e->ref_rms = std::sqrt(acc / static_cast<double>(e->L) + 1e-8);
     return B200X_OK;
 }
 
@@ -380,18 +420,7 @@ extern "C" int b200x_engine_set_track(b200x_engine* e, const float* wave, int64_
     e->n_time = 1 + static_cast<int>(n_samples / e->cfg.hop_length);
     B200X_TRY(b200x_stft(e->wave.as<float>(), n_samples, e->cfg.n_fft, e->cfg.hop_length, 0, e->S.p, b200x_engine::s_stride, e->stream));
     e->launches += 1;
-    // reference RMS for match_rms: sqrt(mean(sig^2) + 1e-8), float64 on the host like the reference (needs the host copy)
-    std::vector<float> tmp;
-    const float* hw = wave;
-    if (on_device) {
-        tmp.resize(n_samples);
-        B200X_CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->wave.p, n_samples * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
-        hw = tmp.data();
-    }
-    double acc = 0.0;
-    for (int64_t i = 0; i < n_samples; ++i) { const float v = hw[i]; acc += static_cast<double>(v * v); }
-    e->ref_rms = std::sqrt(acc / static_cast<double>(n_samples) + 1e-8);
+    e->ref_rms = -1.0;   // computed lazily (ensure_ref_rms) when a loudness-normalised FBP sweep asks for it
     // the tail of every y row beyond hop*(n_time-1) must read as zero padding (spectrogram_explainability.py:679-680)
     B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, e->y.bytes, e->stream));
     return B200X_OK;
@@ -431,7 +460,7 @@ int sweep(b200x_engine* e, int mode, int n, const int32_t* d_windows, float occ_
             sumsq = e->sumsq.as<double>();
             B200X_CUDA_TRY(cudaMemsetAsync(sumsq, 0, m * sizeof(double), e->stream));
         }
-        B200X_TRY(b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, d_windows ? d_windows + 4 * c0 : nullptr,
+        TIMED(KC_ISTFT, b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, d_windows ? d_windows + 4 * c0 : nullptr,
                                      occ_value, d_gains ? d_gains + static_cast<size_t>(c0) * b200x_engine::n_freq : nullptr,
                                      e->y.as<float>(), e->y_stride, sumsq, e->stream));
         e->launches += 1;
@@ -483,6 +512,7 @@ extern "C" int b200x_engine_fbp_sweep(b200x_engine* e, const float* gains, int n
         B200X_CUDA_TRY(cudaMemcpyAsync(e->gains.p, gains, bytes, cudaMemcpyHostToDevice, e->stream));
         d_g = e->gains.as<float>();
     }
+    if (normalize_loudness) B200X_TRY(ensure_ref_rms(e));
     B200X_TRY(sweep(e, B200X_MASK_BAND_GAIN, n, nullptr, 0.f, d_g, normalize_loudness != 0, e->prob.as<float>()));
     B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -519,7 +549,10 @@ extern "C" int b200x_engine_stem_sweep(b200x_engine* e, const float* stems, int 
 }
 
 namespace {
-int audio_out(b200x_engine* e, int mode, const int32_t* windows, const float* gains, int n, float* audio_host) {
+// perturbed audio to the host.  seg_stride > 0: only the window's own time span [t0*hop, t0*hop + max(1,(t1-t0)*hop))
+// clipped to the iSTFT length is copied (row i at audio_host + i*seg_stride, valid length in seg_len[i]).
+int audio_out(b200x_engine* e, int mode, const int32_t* windows, const float* gains, int n, float occ_value, float* audio_host,
+              int64_t seg_stride, int64_t* seg_len) {
     const int64_t out_len = static_cast<int64_t>(e->cfg.hop_length) * (e->n_time - 1);
     if (windows) {
         B200X_TRY(ensure_grow(e->windows, static_cast<size_t>(n) * 16));
@@ -532,30 +565,54 @@ int audio_out(b200x_engine* e, int mode, const int32_t* windows, const float* ga
     }
     for (int c0 = 0; c0 < n; c0 += e->C) {
         const int m = std::min(e->C, n - c0);
-        B200X_TRY(b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, windows ? e->windows.as<int32_t>() + 4 * c0 : nullptr,
-                                     0.f, gains ? e->gains.as<float>() + static_cast<size_t>(c0) * b200x_engine::n_freq : nullptr,
+        TIMED(KC_ISTFT, b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, windows ? e->windows.as<int32_t>() + 4 * c0 : nullptr,
+                                     occ_value, gains ? e->gains.as<float>() + static_cast<size_t>(c0) * b200x_engine::n_freq : nullptr,
                                      e->y.as<float>(), e->y_stride, nullptr, e->stream));
         e->launches += 1;
-        B200X_CUDA_TRY(cudaMemcpy2DAsync(audio_host + static_cast<size_t>(c0) * out_len, out_len * sizeof(float), e->y.p,
-                                         e->y_stride * sizeof(float), out_len * sizeof(float), m, cudaMemcpyDeviceToHost, e->stream));
+        if (seg_stride > 0) {
+            for (int i = 0; i < m; ++i) {
+                const int32_t* w = windows + 4 * (c0 + i);
+                const int64_t want = std::max<int64_t>(1, static_cast<int64_t>(w[1] - w[0]) * e->cfg.hop_length);
+                const int64_t start = std::min<int64_t>(static_cast<int64_t>(w[0]) * e->cfg.hop_length, out_len);
+                const int64_t len = std::min<int64_t>(std::min(start + want, out_len) - start, seg_stride);
+                if (seg_len) seg_len[c0 + i] = len;
+                if (len > 0)
+                    B200X_CUDA_TRY(cudaMemcpyAsync(audio_host + static_cast<size_t>(c0 + i) * seg_stride,
+                                                   e->y.as<float>() + static_cast<size_t>(i) * e->y_stride + start, len * sizeof(float),
+                                                   cudaMemcpyDeviceToHost, e->stream));
+            }
+        } else {
+            B200X_CUDA_TRY(cudaMemcpy2DAsync(audio_host + static_cast<size_t>(c0) * out_len, out_len * sizeof(float), e->y.p,
+                                             e->y_stride * sizeof(float), out_len * sizeof(float), m, cudaMemcpyDeviceToHost, e->stream));
+        }
+        // the next chunk overwrites y: the copies above must have drained first
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
     }
-    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
     return B200X_OK;
 }
 }  // namespace
 
-extern "C" int b200x_engine_window_audio(b200x_engine* e, const int32_t* windows, int n, float* audio_host) {
+extern "C" int b200x_engine_window_audio(b200x_engine* e, const int32_t* windows, int n, float* audio_host,
+                                         int64_t seg_stride, int64_t* seg_len) {
     B200X_TRY(check_ready(e, true));
     if (n == 0) return B200X_OK;
-    B200X_REQUIRE(windows && audio_host && n > 0, "window_audio: bad argument");
-    return audio_out(e, B200X_MASK_KEEP_ONLY, windows, nullptr, n, audio_host);
+    B200X_REQUIRE(windows && audio_host && n > 0 && seg_stride > 0, "window_audio: bad argument");
+    return audio_out(e, B200X_MASK_KEEP_ONLY, windows, nullptr, n, 0.f, audio_host, seg_stride, seg_len);
+}
+
+extern "C" int b200x_engine_occluded_audio(b200x_engine* e, const int32_t* windows, int n, float occlusion_value,
+                                           float* audio_host) {
+    B200X_TRY(check_ready(e, true));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(windows && audio_host && n > 0, "occluded_audio: bad argument");
+    return audio_out(e, B200X_MASK_OCCLUDE, windows, nullptr, n, occlusion_value, audio_host, 0, nullptr);
 }
 
 extern "C" int b200x_engine_band_audio(b200x_engine* e, const float* gains, int n, float* audio_host) {
     B200X_TRY(check_ready(e, true));
     if (n == 0) return B200X_OK;
     B200X_REQUIRE(gains && audio_host && n > 0, "band_audio: bad argument");
-    return audio_out(e, B200X_MASK_BAND_GAIN, nullptr, gains, n, audio_host);
+    return audio_out(e, B200X_MASK_BAND_GAIN, nullptr, gains, n, 0.f, audio_host, 0, nullptr);
 }
 
 extern "C" int b200x_engine_saliency_map(b200x_engine* e, const int32_t* windows, const double* delta, int n,
@@ -636,5 +693,29 @@ extern "C" void* b200x_engine_stream(b200x_engine* e) { return e ? static_cast<v
 extern "C" int b200x_engine_synchronize(b200x_engine* e) {
     B200X_REQUIRE(e != nullptr, "synchronize: engine is NULL");
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_set_timing(b200x_engine* e, int enable) {
+    B200X_REQUIRE(e != nullptr, "set_timing: engine is NULL");
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->timing = enable != 0;
+    e->ev_used = 0;
+    e->ev_class.clear();
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_get_timing(b200x_engine* e, double* ms_per_class, int64_t* launches_per_class) {
+    B200X_REQUIRE(e && ms_per_class && launches_per_class, "get_timing: bad argument");
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < KC_COUNT; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+    for (size_t i = 0; i < e->ev_class.size(); ++i) {
+        float ms = 0.f;
+        B200X_CUDA_TRY(cudaEventElapsedTime(&ms, e->ev_pool[2 * i], e->ev_pool[2 * i + 1]));
+        ms_per_class[e->ev_class[i]] += ms;
+        launches_per_class[e->ev_class[i]] += 1;
+    }
+    e->ev_used = 0;
+    e->ev_class.clear();
     return B200X_OK;
 }

@@ -128,11 +128,23 @@ class Engine:
                    "stem_sweep")
         return prob
 
-    def window_audio(self, windows: np.ndarray) -> np.ndarray:
+    def window_audio(self, windows: np.ndarray) -> list:
+        """Patch-only iSTFT audio of each window, sliced to the window's own time span (list of float32 arrays)."""
+        w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
+        if len(w) == 0:
+            return []
+        hop = self.cfg.hop_length
+        stride = int(max(1, int((w[:, 1] - w[:, 0]).max()) * hop))
+        out = np.zeros((w.shape[0], stride), np.float32)
+        lens = np.zeros(w.shape[0], np.int64)
+        _lib.check(self.lib.b200x_engine_window_audio(self._h, _ptr(w), w.shape[0], _ptr(out), stride, _ptr(lens)), "window_audio")
+        return [out[i, : int(lens[i])].copy() for i in range(w.shape[0])]
+
+    def occluded_audio(self, windows: np.ndarray, occlusion_value: float = 0.0) -> np.ndarray:
         w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
         _, t = self.track_shape()
         out = np.empty((w.shape[0], self.cfg.hop_length * (t - 1)), np.float32)
-        _lib.check(self.lib.b200x_engine_window_audio(self._h, _ptr(w), w.shape[0], _ptr(out)), "window_audio")
+        _lib.check(self.lib.b200x_engine_occluded_audio(self._h, _ptr(w), w.shape[0], float(occlusion_value), _ptr(out)), "occluded_audio")
         return out
 
     def band_audio(self, gains: np.ndarray) -> np.ndarray:
@@ -173,6 +185,18 @@ class Engine:
 
     def set_trace(self, device_ptr: Optional[int]) -> None:
         _lib.check(self.lib.b200x_engine_set_trace(self._h, C.c_void_p(device_ptr or 0)), "set_trace")
+
+    KERNEL_CLASSES = ("istft", "mel", "resize", "gemm", "attention", "layernorm", "head", "other")
+
+    def set_timing(self, enable: bool) -> None:
+        _lib.check(self.lib.b200x_engine_set_timing(self._h, int(enable)), "set_timing")
+
+    def get_timing(self):
+        """{class: (total_ms, launches)} from CUDA events on the engine stream since set_timing / the last call."""
+        ms = np.zeros(8, np.float64)
+        n = np.zeros(8, np.int64)
+        _lib.check(self.lib.b200x_engine_get_timing(self._h, _ptr(ms), _ptr(n)), "get_timing")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     @property
     def launch_count(self) -> int:

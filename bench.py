@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the perturbation-explainability hot path (BASELINE.json: occluded-spectrogram evals/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port), rank 0 only
+
+A "step" is one pass of the hot path over one synthetic 120 s / 16 kHz track (BASELINE configs[1]): baseline
+prediction + the 228-window occlusion sweep (1024-frame x 5 % patches, half-window stride) + the delta-prob ->
+saliency reduction + the four stable top-k rankings + patch-only iSTFT reconstruction of the top windows.
+With N GPUs every rank sweeps its own track (weak scaling: 228 windows per GPU) and ONE NCCL all-gather
+collects the per-window probabilities of all tracks on every rank.
+
+  value : evals/s with the track, its STFT and the window list already resident in HBM (device-side timing, CUDA
+          events on the engine stream, max over ranks)
+  e2e   : the same metric through the public API with HOST buffers: wave upload, window upload, probabilities /
+          saliency map / top-window audio read back, inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR = 16000
+DURATION = 120.0
+PATCH_T, STRIDE_T, PATCH_F, STRIDE_F = 1024, 512, 5.0, 2.5
+TOP_N = 5
+# algorithmic work per perturbed evaluation (2 flops per MAC, padding excluded)
+FLOP_ATTN_PER_EVAL = 12 * 2 * (2 * 1376 * 1376 * 64 * 6)            # QK^T + PV, 12 layers
+FLOP_GEMM_PER_EVAL = 12 * 2 * 1376 * (384 * 1152 + 384 * 384 + 2 * 384 * 1025) + 2 * (1248 * 384 * 384 + 128 * 3744 * 384)
+FLOP_PER_EVAL = FLOP_ATTN_PER_EVAL + FLOP_GEMM_PER_EVAL               # 81.1 GFLOP
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p.get("hbm_gbs", 6650.0), "bf16_tflops": p.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------- CPU baseline / reference arm
+def oracle_evals_per_s(n_evals: int, threads: int):
+    """Times the reference's CPU path (oracle port: librosa-style iSTFT + SpecTTTra forward, fp32, batch 1) on a bounded
+    sample of the same workload: the first ``n_evals`` windows of the sweep, one warm-up eval discarded."""
+    import torch
+    from audio_deepfake_explainability_b200 import grid, synth
+    from audio_deepfake_explainability_b200.weights import ALPHA_120S, random_state_dict
+    from oracle import dsp, spectttra                      # CPU baseline leg: the one place bench.py executes oracle/
+
+    torch.set_num_threads(threads)
+    y = synth.synth_track("REAL", 0, SR, DURATION)
+    sd = random_state_dict(ALPHA_120S, 0)
+    pred = spectttra.OraclePredictor(sd, ALPHA_120S, "fp32")
+    S = dsp.stft(y).numpy()
+    wins = grid.occlusion_windows(S.shape[0], S.shape[1], PATCH_T, STRIDE_T, PATCH_F, STRIDE_F)
+    base = pred.predict(y, SR)
+
+    def one(w):
+        t0, t1, f0, f1 = w
+        patch = S[f0:f1, t0:t1].copy()
+        S[f0:f1, t0:t1] = 0.0
+        y_occ = dsp.istft(S).numpy()
+        S[f0:f1, t0:t1] = patch
+        return base - pred.predict(y_occ, SR)
+
+    one(wins[0])
+    t = time.perf_counter()
+    for i in range(n_evals):
+        one(wins[(1 + i) % len(wins)])
+    dt = time.perf_counter() - t
+    return n_evals / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    threads = os.cpu_count() or 1
+    per_step = 4                                            # bounded sample: 4 perturbed evals per step
+    for _ in range(args.warmup):
+        oracle_evals_per_s(1, threads)
+    rates, times = [], []
+    for _ in range(args.steps):
+        r, dt = oracle_evals_per_s(per_step, threads)
+        rates.append(r)
+        times.append(dt)
+    value = per_step * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": "occluded-spectrogram evals/sec", "value": value, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, None),
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{per_step} perturbed evals per step (iSTFT + SpecTTTra forward, batch 1) of the 228-window sweep"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus: int, chunk):
+    return {"workload": "configs[1]: occlusion sweep, one synthetic 120 s 16 kHz track per GPU, random-init SpecTTTra-alpha-120s, "
+                        "1024-frame x 5% window, half-window stride (228 evals) + baseline + saliency map + top-5 window iSTFT",
+            "windows_per_track": 228, "tracks": n_gpus, "copies_per_chunk": chunk,
+            "l2_policy": "inputs larger than L2: each step streams 228 x (30.8 MB spectrogram reads + 7.7 MB waveform) and "
+                         ">100 MB of activations per chunk",
+            "parallelism": f"windows/tracks sharded over {n_gpus} GPU(s), one NCCL all-gather of probabilities"}
+
+
+# --------------------------------------------------------------------------------------------- engine arm
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from audio_deepfake_explainability_b200 import grid, synth
+    from audio_deepfake_explainability_b200.engine import Engine
+    from audio_deepfake_explainability_b200.weights import ALPHA_120S, random_state_dict
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = read_peaks()
+
+    cfg = ALPHA_120S
+    eng = Engine(cfg, random_state_dict(cfg, 0), copies_per_chunk=args.chunk, max_samples=int(SR * DURATION), device=local)
+    fam = synth.FAMILIES[rank % len(synth.FAMILIES)]
+    y = synth.synth_track(fam, rank // len(synth.FAMILIES), SR, DURATION)
+    n_freq, n_time = grid.stft_shape(len(y), 2048, 512)
+    windows = grid.occlusion_windows(n_freq, n_time, PATCH_T, STRIDE_T, PATCH_F, STRIDE_F)
+    n_win = len(windows)
+    assert n_win == 228
+    y_pin = torch.from_numpy(y).pin_memory()
+    win_pin = torch.from_numpy(windows).pin_memory()
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+    lib = eng.lib
+    from audio_deepfake_explainability_b200 import _lib
+    import ctypes as C
+
+    # ---- device-resident step ------------------------------------------------------------------
+    d_wave = torch.from_numpy(y).cuda()
+    d_win = torch.from_numpy(windows).cuda()
+    d_prob = torch.zeros(n_win, device="cuda")
+    d_base = torch.zeros(1, device="cuda")
+    d_delta = torch.zeros(n_win, dtype=torch.float64, device="cuda")
+    d_map = torch.zeros(n_freq, n_time, dtype=torch.float64, device="cuda")
+    d_order = torch.zeros(4, n_win, dtype=torch.int32, device="cuda")
+    gather_buf = [torch.zeros(n_win, device="cuda") for _ in range(world)]
+    torch.cuda.synchronize()
+    sp = C.c_void_p(eng.stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+
+    def device_step():
+        _lib.check(lib.b200x_engine_set_track(eng._h, P(d_wave), len(y), 1), "set_track")
+        _lib.check(lib.b200x_engine_predict(eng._h, P(d_wave), len(y), 1, 1, P(d_base), None), "predict")
+        _lib.check(lib.b200x_engine_occlusion_sweep(eng._h, P(d_win), n_win, 0.0, 1, P(d_prob)), "sweep")
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather(gather_buf, d_prob)
+        base = float(d_base.item())
+        _lib.check(lib.b200x_delta(P(d_prob), base, n_win, P(d_delta), sp), "delta")
+        _lib.check(lib.b200x_saliency_reduce(P(d_win), P(d_delta), n_win, n_freq, n_time, P(d_map), sp), "saliency")
+        for mode in range(4):
+            _lib.check(lib.b200x_rank(P(d_delta), n_win, mode, P(d_order[mode]), sp), "rank")
+        order = d_order.cpu().numpy()
+        top = np.unique(np.concatenate([order[0][:TOP_N], order[1][:TOP_N], order[2][:TOP_N], order[3][:TOP_N]]))
+        eng.window_audio(windows[top])
+        return 6                                            # delta + saliency + 4 rank kernels launched outside the engine's own counter
+
+    def host_step():
+        eng.set_track(y_pin.numpy())
+        base = float(eng.predict(y_pin.numpy()))
+        prob = eng.occlusion_sweep(win_pin.numpy(), 0.0)
+        if world > 1:
+            t = torch.from_numpy(prob).cuda()
+            dist.all_gather(gather_buf, t)
+        delta = np.float64(np.float32(base)) - prob.astype(np.float64)
+        sal = eng.saliency_map(windows, delta)
+        orders = [eng.rank(delta, m) for m in range(4)]
+        top = np.unique(np.concatenate([o[:TOP_N] for o in orders]))
+        aud = eng.window_audio(windows[top])
+        h2d = 2 * y.nbytes + windows.nbytes + windows.nbytes + delta.nbytes + 4 * delta.nbytes + windows[top].nbytes
+        d2h = prob.nbytes + 4 + sal.nbytes + 4 * 4 * n_win + sum(a.nbytes for a in aud)
+        return h2d, d2h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(stream)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        ms = max(dev_ms, 0.0)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms, wall, out
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    l0 = eng.launch_count
+    with ClockSampler(local) as clk:
+        ms_dev, wall_dev, extra = timed(device_step, args.steps)
+    launches = (eng.launch_count - l0) + extra * args.steps
+    for _ in range(2):
+        host_step()
+    ms_host, wall_host, io = timed(host_step, args.steps)
+    # the e2e number is host-visible time: the calls block on the host, so use the wall clock when it is larger
+    ms_host = max(ms_host, 1e3 * wall_host)
+    if world > 1:
+        t = torch.tensor([ms_host], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_host = float(t.item())
+
+    evals_per_step = (n_win + 1) * world                   # perturbed copies + the baseline evaluation, all ranks
+    value = evals_per_step * args.steps / (ms_dev * 1e-3)
+    e2e = evals_per_step * args.steps / (ms_host * 1e-3)
+
+    # ---- roofline of the dominant kernel: per-class CUDA-event timing over one more timed pass ---
+    eng.set_timing(True)
+    for _ in range(max(1, min(args.steps, 3))):
+        device_step()
+    tim = eng.get_timing()
+    eng.set_timing(False)
+    n_pass = max(1, min(args.steps, 3))
+    total_ms = sum(v[0] for v in tim.values())
+    shares = {k: (v[0] / total_ms if total_ms else 0.0) for k, v in tim.items()}
+    dom = max(("attention", "gemm"), key=lambda k: tim[k][0])
+    evals_timed = (n_win + 1) * n_pass
+    flops = (FLOP_ATTN_PER_EVAL if dom == "attention" else FLOP_GEMM_PER_EVAL) * evals_timed
+    dom_ms, dom_n = tim[dom]
+    achieved = flops / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
+    roofline = {"bound": "tensor", "kernel": "attention_kernel" if dom == "attention" else "gemm_bf16_tn_kernel",
+                "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": f"{peaks['source']} (sustained bf16; kernel timed inside a long step)",
+                "avg_launch_ms": dom_ms / dom_n if dom_n else None, "launches": dom_n,
+                "algorithmic_flops_per_launch": flops / dom_n if dom_n else None,
+                "share_of_step": shares, "ms_per_class": {k: v[0] / n_pass for k, v in tim.items()},
+                "whole_forward_frac_of_peak": (FLOP_PER_EVAL * evals_per_step / world * args.steps / (ms_dev * 1e-3) / 1e12)
+                / peaks["bf16_tflops_sustained"]}
+
+    line = None
+    if rank == 0:
+        cpu_rate, cpu_dt = (None, None)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            import torch as _t
+            threads = os.cpu_count() or 1
+            cpu_rate, cpu_dt = oracle_evals_per_s(args.cpu_evals, threads)
+            cpu = {"value": cpu_rate, "unit": "evals/s", "cores": _t.get_num_threads(), "kind": "port",
+                   "sample": f"{args.cpu_evals} perturbed evals of the same 228-window sweep (oracle: iSTFT + SpecTTTra fp32, batch 1), {cpu_dt:.1f} s"}
+        line = {
+            "metric": "occluded-spectrogram evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world, args.chunk),
+            "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
+                    "ms_per_step": ms_host / args.steps},
+            "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--chunk", type=int, default=16, help="perturbed copies per pass (L2-resident working set)")
+    ap.add_argument("--cpu-evals", type=int, default=10, help="bounded CPU-baseline sample (perturbed evals)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

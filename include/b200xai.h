@@ -164,9 +164,14 @@ int b200x_engine_fbp_sweep(b200x_engine* e, const float* gains, int n, int norma
 /* AudioLIME recombinations (src/lime_explainer.py:283-301): stems float [n_stems][n_samples], masks uint8 [n][n_stems]. */
 int b200x_engine_stem_sweep(b200x_engine* e, const float* stems, int n_stems, int64_t n_samples, const uint8_t* masks,
                             int n, int on_device, float* prob);
-/* Top-window audio reconstructed from the patch alone (src/spectrogram_explainability.py:472-483):
- * audio float [n][hop*(n_time-1)] host. */
-int b200x_engine_window_audio(b200x_engine* e, const int32_t* windows, int n, float* audio_host);
+/* Top-window audio reconstructed from the patch alone (src/spectrogram_explainability.py:472-483): row i of audio_host
+ * (stride seg_stride floats) receives y_patch[t0*hop : min(t0*hop + max(1,(t1-t0)*hop), hop*(n_time-1))]; its length is
+ * written to seg_len[i] (nullable). */
+int b200x_engine_window_audio(b200x_engine* e, const int32_t* windows, int n, float* audio_host, int64_t seg_stride,
+                              int64_t* seg_len);
+/* Full occluded waveforms istft(S with window i := value): float [n][hop*(n_time-1)] host (lets a foreign duck-typed
+ * predictor consume the GPU DSP stage; src/spectrogram_explainability.py:670-680). */
+int b200x_engine_occluded_audio(b200x_engine* e, const int32_t* windows, int n, float occlusion_value, float* audio_host);
 /* Perturbed audio of the FBP bands (for separated_bands WAVs, src/dsp_band_ops.py:608-639): float [n][hop*(n_time-1)]. */
 int b200x_engine_band_audio(b200x_engine* e, const float* gains, int n, float* audio_host);
 
@@ -180,6 +185,10 @@ int b200x_engine_rank(b200x_engine* e, const double* values, int n, int mode, in
 int b200x_engine_debug_buffer(b200x_engine* e, const char* name, void** d_ptr, int64_t* bytes);
 int b200x_engine_set_trace(b200x_engine* e, float* d_trace /* [layers+1][copies*tokens][dim] or NULL */);
 int64_t b200x_engine_launch_count(b200x_engine* e);
+/* per-kernel-class CUDA-event timing on the engine stream: classes 0 istft, 1 mel, 2 normalise/resize, 3 gemm,
+ * 4 attention, 5 layernorm, 6 head, 7 other; get_timing returns the sums since set_timing / the last get (8 entries). */
+int b200x_engine_set_timing(b200x_engine* e, int enable);
+int b200x_engine_get_timing(b200x_engine* e, double* ms_per_class, int64_t* launches_per_class);
 void* b200x_engine_stream(b200x_engine* e);
 int b200x_engine_synchronize(b200x_engine* e);
 

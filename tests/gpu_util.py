@@ -27,3 +27,18 @@ def ok(status, what=""):
 
 def bf16_round(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
+
+
+_KEEP = []
+
+
+def D(x):
+    """Upload a tensor / array to the GPU and keep it alive until the process ends (a temporary passed straight to
+    P() would be freed - and its block reused by the next temporary - before the kernel runs)."""
+    t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+    t = t.cuda()
+    _KEEP.append(t)
+    if len(_KEEP) > 64:
+        torch.cuda.synchronize()
+        del _KEEP[:32]
+    return t

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from gpu_util import P, lib, ok
+from gpu_util import D, P, lib, ok
 
 pytestmark = pytest.mark.gpu
 
@@ -23,7 +23,7 @@ def test_attention_matches_reference(copies, tokens, heads, scale):
     qkv = (torch.randn(copies * tokens, 3 * heads * 64, generator=g) * scale).to(torch.bfloat16)
     ref = _ref(qkv, copies, tokens, heads)
     out = torch.full((copies * tokens, heads * 64), float("nan"), dtype=torch.bfloat16, device="cuda")
-    ok(lib().b200x_attention(P(qkv.cuda()), P(out), copies, tokens, heads, 64, P(None)))
+    ok(lib().b200x_attention(P(D(qkv)), P(out), copies, tokens, heads, 64, P(None)))
     got = out.float().cpu()
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()

@@ -5,7 +5,7 @@ import torch
 
 from audio_deepfake_explainability_b200 import grid, synth
 from audio_deepfake_explainability_b200.weights import ALPHA_120S
-from gpu_util import P, lib, ok
+from gpu_util import D, P, lib, ok
 from oracle import dsp, spectttra
 
 pytestmark = pytest.mark.gpu
@@ -20,7 +20,7 @@ def _track(seconds=8.0, family="REAL", extra=0):
 def _gpu_stft(y, reflect=0):
     n_frames = 1 + len(y) // 512
     S = torch.zeros(n_frames, STRIDE, 2, device="cuda")
-    ok(lib().b200x_stft(P(torch.from_numpy(y).cuda()), len(y), 2048, 512, reflect, P(S), STRIDE, P(None)))
+    ok(lib().b200x_stft(P(D(y)), len(y), 2048, 512, reflect, P(S), STRIDE, P(None)))
     return S
 
 
@@ -163,6 +163,6 @@ def test_mix_stems():
     st = np.stack([stems[k] for k in sorted(stems)])
     masks = np.array([[1, 1, 1, 1], [0, 0, 0, 0], [1, 0, 1, 0], [0, 1, 0, 0]], np.uint8)
     out = torch.full((4, st.shape[1]), float("nan"), device="cuda")
-    ok(lib().b200x_mix_stems(P(torch.from_numpy(st).cuda()), st.shape[1], 4, P(torch.from_numpy(masks).cuda()), 4, P(out), st.shape[1], P(None)))
+    ok(lib().b200x_mix_stems(P(D(st)), st.shape[1], 4, P(D(masks)), 4, P(out), st.shape[1], P(None)))
     ref = masks.astype(np.float32) @ st
     assert np.abs(out.cpu().numpy() - ref).max() < 1e-6

@@ -38,7 +38,7 @@ def test_forward_stages_match_oracle(eng, sd):
         eng.set_trace(None)
     t = torch.from_numpy(y).unsqueeze(0)
     img = spectttra.resize(dsp.mel_frontend(t, CFG), CFG)
-    for mode, tol_tok, tol_layer, tol_logit in (("bf16", 2e-3, 3e-2, 3e-3), ("fp32", 3e-2, 1e-1, 1.5e-2)):
+    for mode, tol_tok, tol_layer, tol_logit in (("bf16", 6e-3, 3e-2, 3e-3), ("fp32", 3e-2, 1e-1, 1.5e-2)):
         tok = spectttra.tokenize(img, sd, CFG, mode)
         _, layers = spectttra.encoder(tok, sd, CFG, mode, return_all=True)
         e0 = (trace[0].cpu() - tok[0]).abs().max().item()
@@ -96,8 +96,8 @@ def test_occlusion_sweep_matches_oracle(eng, sd):
     for i in range(2):
         p = dict(t_start=int(sel[i][0]), t_end=int(sel[i][1]), f_start=int(sel[i][2]), f_end=int(sel[i][3]))
         ref = loops.window_audio(y, S_ref, p, 512, 2048, use_original_audio=False)
-        start = p["t_start"] * 512
-        assert np.abs(aud[i][start:start + len(ref)] - ref).max() < 3e-6
+        assert aud[i].shape == ref.shape
+        assert np.abs(aud[i] - ref).max() < 3e-6
 
 
 @pytest.mark.parametrize("normalize", [False, True])

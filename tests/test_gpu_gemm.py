@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from gpu_util import P, bf16_round, lib, ok
+from gpu_util import D, P, bf16_round, lib, ok
 
 pytestmark = pytest.mark.gpu
 OUT_BF16, OUT_RESID, OUT_TOKEN = 0, 1, 2
@@ -38,7 +38,7 @@ def _run(M, N, K, bn, mode, bias=True, gelu=False, group=None, lda=None, seed=0)
         pe = torch.randn(gin, N, generator=g)
         copies = M // gin
         out = torch.zeros(copies * gout, N, device="cuda")
-        ok(lib().b200x_gemm_bf16(P(da), lda, P(dw), K, M, N, K, bn, P(out), N, mode, P(db), int(gelu), P(None), P(pe.cuda()), gin, gout, goff, P(None)))
+        ok(lib().b200x_gemm_bf16(P(da), lda, P(dw), K, M, N, K, bn, P(out), N, mode, P(db), int(gelu), P(None), P(D(pe)), gin, gout, goff, P(None)))
         full = out.cpu().reshape(copies, gout, N)
         got = full[:, goff:goff + gin].reshape(M, N)
         ref = (ref.reshape(copies, gin, N) + pe).reshape(M, N)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from audio_deepfake_explainability_b200 import grid
-from gpu_util import P, lib, ok
+from gpu_util import D, P, lib, ok
 from oracle import loops
 
 pytestmark = pytest.mark.gpu
@@ -16,11 +16,11 @@ def test_layernorm_bf16_and_inplace_groups():
     ga, ba = torch.randn(384, generator=g), torch.randn(384, generator=g)
     gb, bb = torch.randn(384, generator=g), torch.randn(384, generator=g)
     out = torch.zeros(x.shape, dtype=torch.bfloat16, device="cuda")
-    ok(lib().b200x_layernorm(P(x.cuda()), x.shape[0], 384, P(ga.cuda()), P(ba.cuda()), P(None), P(None), 0, 0, 1e-5, P(out), P(None), P(None)))
+    ok(lib().b200x_layernorm(P(D(x)), x.shape[0], 384, P(D(ga)), P(D(ba)), P(None), P(None), 0, 0, 1e-5, P(out), P(None), P(None)))
     ref = torch.nn.functional.layer_norm(x, (384,), ga, ba, 1e-5)
     assert (out.float().cpu() - ref).abs().max().item() < 3e-2
     xi = x[: 2 * 1376].cuda().clone()
-    ok(lib().b200x_layernorm(P(xi), 2 * 1376, 384, P(ga.cuda()), P(ba.cuda()), P(gb.cuda()), P(bb.cuda()), 1376, 1248, 1e-6, P(None), P(xi), P(None)))
+    ok(lib().b200x_layernorm(P(xi), 2 * 1376, 384, P(D(ga)), P(D(ba)), P(D(gb)), P(D(bb)), 1376, 1248, 1e-6, P(None), P(xi), P(None)))
     xr = x[: 2 * 1376].reshape(2, 1376, 384)
     ref2 = torch.cat([torch.nn.functional.layer_norm(xr[:, :1248], (384,), ga, ba, 1e-6),
                       torch.nn.functional.layer_norm(xr[:, 1248:], (384,), gb, bb, 1e-6)], dim=1).reshape(-1, 384)
@@ -34,7 +34,7 @@ def test_head_matches_reference(use_norm):
     ga, ba, w = torch.randn(384, generator=g), torch.randn(384, generator=g), torch.randn(384, generator=g) * 0.05
     part = torch.zeros(3 * lib().b200x_head_slices(), device="cuda")
     logit, prob = torch.zeros(3, device="cuda"), torch.zeros(3, device="cuda")
-    ok(lib().b200x_head(P(x.cuda()), 3, 1376, 384, P(ga.cuda()), P(ba.cuda()), 1e-5, use_norm, P(w.cuda()), 0.3, P(part), P(logit), P(prob), P(None)))
+    ok(lib().b200x_head(P(D(x)), 3, 1376, 384, P(D(ga)), P(D(ba)), 1e-5, use_norm, P(D(w)), 0.3, P(part), P(logit), P(prob), P(None)))
     f = torch.nn.functional.layer_norm(x, (384,), ga, ba, 1e-5) if use_norm else x
     ref = f.mean(1) @ w + 0.3
     assert (logit.cpu() - ref).abs().max().item() < 1e-5
@@ -48,7 +48,7 @@ def test_saliency_map_bit_exact(stride_t, sf):
     rng = np.random.default_rng(len(wins))
     delta = rng.standard_normal(len(wins)) * 1e-2
     out = torch.full((n_freq, n_time), float("nan"), dtype=torch.float64, device="cuda")
-    ok(lib().b200x_saliency_reduce(P(torch.from_numpy(wins).cuda()), P(torch.from_numpy(delta).cuda()), len(wins), n_freq, n_time, P(out), P(None)))
+    ok(lib().b200x_saliency_reduce(P(D(wins)), P(D(delta)), len(wins), n_freq, n_time, P(out), P(None)))
     ref = loops.saliency_from_windows(wins, delta, n_freq, n_time)
     assert np.array_equal(out.cpu().numpy(), ref)                            # float64, same order -> identical bits
 
@@ -59,7 +59,7 @@ def test_saliency_map_empty_and_ragged():
     assert (out == 0).all()
     wins = np.array([[0, 130, 0, 7], [129, 130, 6, 7], [3, 3, 1, 2]], np.int32)
     d = np.array([0.5, -0.25, 9.0])
-    ok(lib().b200x_saliency_reduce(P(torch.from_numpy(wins).cuda()), P(torch.from_numpy(d).cuda()), 3, 7, 130, P(out), P(None)))
+    ok(lib().b200x_saliency_reduce(P(D(wins)), P(D(d)), 3, 7, 130, P(out), P(None)))
     assert np.array_equal(out.cpu().numpy(), loops.saliency_from_windows(wins, d, 7, 130))
 
 
@@ -68,7 +68,7 @@ def test_band_map_bit_exact():
     rows = grid.band_bin_ranges(bands, 16000, 2048)
     delta = np.random.default_rng(3).standard_normal(len(bands))
     out = torch.zeros((1025, 500), dtype=torch.float64, device="cuda")
-    ok(lib().b200x_band_map(P(torch.from_numpy(rows).cuda()), P(torch.from_numpy(delta).cuda()), len(bands), 1025, 500, P(out), P(None)))
+    ok(lib().b200x_band_map(P(D(rows)), P(D(delta)), len(bands), 1025, 500, P(out), P(None)))
     freqs = grid.fft_frequencies(16000, 2048)
     ref = np.zeros((1025, 500))
     for (lo, hi), d in zip(bands, delta):
@@ -82,7 +82,7 @@ def test_rank_is_stable_like_python_sorted(mode, key, desc):
     v = np.round(rng.standard_normal(825), 1)                                # many exact ties
     v[::50] = 0.0
     order = torch.zeros(len(v), dtype=torch.int32, device="cuda")
-    ok(lib().b200x_rank(P(torch.from_numpy(v).cuda()), len(v), mode, P(order), P(None)))
+    ok(lib().b200x_rank(P(D(v)), len(v), mode, P(order), P(None)))
     ref = sorted(range(len(v)), key=lambda i: key(v[i]), reverse=desc)
     assert order.cpu().tolist() == ref
 
