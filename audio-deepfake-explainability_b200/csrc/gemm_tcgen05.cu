@@ -33,7 +33,9 @@ struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = GEMM_STAGES * STAGE_BYTES;
+    static constexpr int EPI_OFFSET = GEMM_STAGES * STAGE_BYTES;          // 4 epilogue warps x [32 rows][36 floats]
+    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
     static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
 };
@@ -126,74 +128,71 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // TMEM lane == tile row, so tcgen05.ld hands every thread one row.  The chunk is transposed through a padded,
+        // warp-private shared-memory tile so that global traffic is row-contiguous (a quarter-warp covers 128 bytes of one
+        // output row) - bias / GELU / positional encoding / residual are applied on that coalesced side.
         const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter + 32)
+        float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + quarter * (32 * 36);
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-            const int m = m_blk * GEMM_BM + quarter * 32 + lane;
-            const bool row_ok = m < p.M;
-            long long out_row = m;
-            int g_idx = 0;
-            if (p.group_in > 0) {
-                g_idx = m % p.group_in;
-                out_row = static_cast<long long>(m / p.group_in) * p.group_out + p.group_off + g_idx;
-            }
+            const int m_warp = m_blk * GEMM_BM + quarter * 32;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t r[16];
-                tmem_ld16(t_row + c, r);
+            for (int c = 0; c < BN; c += 32) {
+                const bool wide = (c + 32 <= BN);        // BN = 208 ends with a 16-column chunk
+                const int cw = wide ? 32 : 16;
+                const int ld = cw + 4;                   // padded row stride (floats) of the staging tile
+                uint32_t r[32];
+                if (wide) tmem_ld32(t_row + c, r); else tmem_ld16(t_row + c, r);
                 tmem_wait_ld();
-                const int n0 = n_blk * BN + c;
-                if (row_ok && n0 < p.N) {
-                    float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                    if (p.bias != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + i);
-                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                for (int i = 0; i < 32; i += 4)
+                    if (i < cw)
+                        *reinterpret_cast<uint4*>(stage + lane * ld + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                __syncwarp();
+                const int lpr = cw / 4;                  // lanes per row (float4 each)
+                const int rpi = 32 / lpr;                // rows per warp instruction
+                const int col = (lane % lpr) * 4;
+                const int n0 = n_blk * BN + c + col;
+                if (n0 < p.N) {
+                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(p.bias + n0);
+                    for (int it = 0; it < 32; it += rpi) {
+                        const int row = it + lane / lpr;
+                        const int m = m_warp + row;
+                        if (m >= p.M) continue;
+                        float4 v = *reinterpret_cast<const float4*>(stage + row * ld + col);
+                        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                        if (p.act_gelu) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
+                        long long out_row = m;
+                        int g_idx = 0;
+                        if (p.group_in > 0) {
+                            g_idx = m % p.group_in;
+                            out_row = static_cast<long long>(m / p.group_in) * p.group_out + p.group_off + g_idx;
                         }
-                    }
-                    if (p.act_gelu) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-                    }
-                    if (p.out_mode == B200X_GEMM_OUT_BF16) {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n0;
-                        uint4 w0, w1;
-                        w0.x = pack_bf16(v[0], v[1]);   w0.y = pack_bf16(v[2], v[3]);
-                        w0.z = pack_bf16(v[4], v[5]);   w0.w = pack_bf16(v[6], v[7]);
-                        w1.x = pack_bf16(v[8], v[9]);   w1.y = pack_bf16(v[10], v[11]);
-                        w1.z = pack_bf16(v[12], v[13]); w1.w = pack_bf16(v[14], v[15]);
-                        reinterpret_cast<uint4*>(o)[0] = w0;
-                        reinterpret_cast<uint4*>(o)[1] = w1;
-                    } else {
-                        float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldc + n0;
-                        if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
-                            const float* rs = p.resid + out_row * p.ldc + n0;
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 x = *reinterpret_cast<const float4*>(rs + i);
-                                v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
+                        if (p.out_mode == B200X_GEMM_OUT_BF16) {
+                            uint2 w;
+                            w.x = pack_bf16(v.x, v.y);
+                            w.y = pack_bf16(v.z, v.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n0) = w;
+                        } else {
+                            float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldc + n0;
+                            if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
+                                const float4 x = *reinterpret_cast<const float4*>(p.resid + out_row * p.ldc + n0);
+                                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+                            } else if (p.pe != nullptr) {
+                                const float4 x = *reinterpret_cast<const float4*>(p.pe + static_cast<long long>(g_idx) * p.N + n0);
+                                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
                             }
-                        } else if (p.pe != nullptr) {
-                            const float* pe = p.pe + static_cast<long long>(g_idx) * p.N + n0;
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const float4 x = *reinterpret_cast<const float4*>(pe + i);
-                                v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
-                            }
+                            *reinterpret_cast<float4*>(o) = v;
                         }
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -239,6 +238,7 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
                                void* stream) {
     B200X_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B200X_REQUIRE(N % 16 == 0, "gemm: N=%d must be a multiple of 16", N);
+    B200X_REQUIRE(d_bias == nullptr || (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0, "gemm: bias not 16-byte aligned");
     B200X_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda=%d / ldw=%d must be multiples of 8 (16-byte rows)", lda, ldw);
     B200X_REQUIRE(out_mode >= B200X_GEMM_OUT_BF16 && out_mode <= B200X_GEMM_OUT_F32_TOKEN, "gemm: bad out_mode %d", out_mode);
     B200X_REQUIRE(out_mode != B200X_GEMM_OUT_F32_RESID || d_resid != nullptr, "gemm: residual pointer missing");
