@@ -1,8 +1,10 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] . W[N,K]^T  (+ fused epilogue)
 //
-//   warp 0 : TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring)
+//   warp 0 : TMA producer (cp.async.bulk.tensor, 128B swizzle, 3/4-stage mbarrier ring)
 //   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate in TMEM)
-//   warps 2-5 : epilogue (tcgen05.ld -> registers -> fused bias / GELU / positional-encoding / residual -> global)
+//   warps 2-9 : epilogue (tcgen05.ld -> registers -> smem transpose -> fused bias / GELU / positional-encoding /
+//               residual on coalesced rows -> global); with K = 384 the epilogue is as long as the MMAs, so it gets
+//               8 warps and batched (unrolled) global accesses
 //
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.  Used for every dense
 // contraction of the SpecTTTra forward (tokenizer projections, QKV, attention projection, MLP).
@@ -13,8 +15,8 @@ namespace b200x {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;      // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                       // two warps per TMEM lane quarter (they split the columns)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 
 struct GemmParams {
     int M, N, K;
@@ -30,15 +32,78 @@ struct GemmParams {
 
 template <int BN>
 struct GemmSmem {
+    static constexpr int STAGES = BN > 208 ? 3 : 4;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_OFFSET = GEMM_STAGES * STAGE_BYTES;          // 4 epilogue warps x [32 rows][36 floats]
-    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;               // per epilogue warp: [32 rows][36 floats]
+    static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * 36 * 4;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
     static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
 };
+
+// One staged chunk of CW columns: the warp's 32 rows sit in `stage` (row stride CW + 4 floats); a group of CW/4 lanes
+// covers one row with float4s.  All shared / global loads of the chunk are issued before any of them is consumed.
+template <int CW>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* stage, int lane, int m_warp, int n_base) {
+    constexpr int LD = CW + 4, LPR = CW / 4, RPI = 32 / LPR, NIT = 32 / RPI;
+    const int col = (lane % LPR) * 4;
+    const int n0 = n_base + col;
+    if (n0 >= p.N) return;
+    float4 v[NIT];
+    int orow[NIT];
+    int gidx[NIT];
+    bool okr[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int row = it * RPI + lane / LPR;
+        const int m = m_warp + row;
+        okr[it] = m < p.M;
+        v[it] = *reinterpret_cast<const float4*>(stage + row * LD + col);
+        orow[it] = m;
+        gidx[it] = 0;
+        if (p.group_in > 0) {
+            gidx[it] = m % p.group_in;
+            orow[it] = (m / p.group_in) * p.group_out + p.group_off + gidx[it];
+        }
+    }
+    float4 add[NIT];
+    const bool has_add = (p.out_mode == B200X_GEMM_OUT_F32_RESID) || (p.out_mode == B200X_GEMM_OUT_F32_TOKEN && p.pe != nullptr);
+    if (has_add) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            add[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (okr[it]) {
+                const float* src = (p.out_mode == B200X_GEMM_OUT_F32_RESID) ? p.resid + static_cast<long long>(orow[it]) * p.ldc + n0
+                                                                           : p.pe + static_cast<long long>(gidx[it]) * p.N + n0;
+                add[it] = *reinterpret_cast<const float4*>(src);
+            }
+        }
+    }
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        float4 x = v[it];
+        x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+        if (p.act_gelu) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
+        if (has_add) { x.x += add[it].x; x.y += add[it].y; x.z += add[it].z; x.w += add[it].w; }
+        v[it] = x;
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        if (!okr[it]) continue;
+        if (p.out_mode == B200X_GEMM_OUT_BF16) {
+            uint2 w;
+            w.x = pack_bf16(v[it].x, v[it].y);
+            w.y = pack_bf16(v[it].z, v[it].w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(orow[it]) * p.ldc + n0) = w;
+        } else {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(orow[it]) * p.ldc + n0) = v[it];
+        }
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -47,6 +112,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int GEMM_STAGES = L::STAGES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + GEMM_STAGES;
     uint64_t* tfull_bar = empty_bar + GEMM_STAGES;
@@ -69,7 +135,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);
+            mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -127,12 +193,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        // TMEM lane == tile row, so tcgen05.ld hands every thread one row.  The chunk is transposed through a padded,
-        // warp-private shared-memory tile so that global traffic is row-contiguous (a quarter-warp covers 128 bytes of one
-        // output row) - bias / GELU / positional encoding / residual are applied on that coalesced side.
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // TMEM lane == tile row, so tcgen05.ld hands every thread one row.  Each 32-column chunk is transposed through a
+        // padded, warp-private shared-memory tile so that global traffic is row-contiguous; two warps per lane quarter and
+        // fully unrolled (batched) shared / global accesses keep enough requests in flight to hide their latency.
         const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter + 32)
-        float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + quarter * (32 * 36);
+        const int half = (warp - 2) >> 2;                // which of the two warps sharing this lane quarter
+        float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 2) * (32 * 36);
+        constexpr int NCHUNK = (BN + 31) / 32;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -142,56 +210,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int m_warp = m_blk * GEMM_BM + quarter * 32;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int ci = half; ci < NCHUNK; ci += 2) {
+                const int c = ci * 32;
                 const bool wide = (c + 32 <= BN);        // BN = 208 ends with a 16-column chunk
-                const int cw = wide ? 32 : 16;
-                const int ld = cw + 4;                   // padded row stride (floats) of the staging tile
                 uint32_t r[32];
                 if (wide) tmem_ld32(t_row + c, r); else tmem_ld16(t_row + c, r);
                 tmem_wait_ld();
+                if (wide) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    if (i < cw)
-                        *reinterpret_cast<uint4*>(stage + lane * ld + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-                __syncwarp();
-                const int lpr = cw / 4;                  // lanes per row (float4 each)
-                const int rpi = 32 / lpr;                // rows per warp instruction
-                const int col = (lane % lpr) * 4;
-                const int n0 = n_blk * BN + c + col;
-                if (n0 < p.N) {
-                    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(p.bias + n0);
-                    for (int it = 0; it < 32; it += rpi) {
-                        const int row = it + lane / lpr;
-                        const int m = m_warp + row;
-                        if (m >= p.M) continue;
-                        float4 v = *reinterpret_cast<const float4*>(stage + row * ld + col);
-                        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-                        if (p.act_gelu) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
-                        long long out_row = m;
-                        int g_idx = 0;
-                        if (p.group_in > 0) {
-                            g_idx = m % p.group_in;
-                            out_row = static_cast<long long>(m / p.group_in) * p.group_out + p.group_off + g_idx;
-                        }
-                        if (p.out_mode == B200X_GEMM_OUT_BF16) {
-                            uint2 w;
-                            w.x = pack_bf16(v.x, v.y);
-                            w.y = pack_bf16(v.z, v.w);
-                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n0) = w;
-                        } else {
-                            float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldc + n0;
-                            if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
-                                const float4 x = *reinterpret_cast<const float4*>(p.resid + out_row * p.ldc + n0);
-                                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
-                            } else if (p.pe != nullptr) {
-                                const float4 x = *reinterpret_cast<const float4*>(p.pe + static_cast<long long>(g_idx) * p.N + n0);
-                                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
-                            }
-                            *reinterpret_cast<float4*>(o) = v;
-                        }
-                    }
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<uint4*>(stage + lane * 36 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<uint4*>(stage + lane * 20 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
                 }
+                __syncwarp();
+                if (wide) epilogue_chunk<32>(p, stage, lane, m_warp, n_blk * BN + c);
+                else epilogue_chunk<16>(p, stage, lane, m_warp, n_blk * BN + c);
                 __syncwarp();
             }
             tc_fence_before();
