@@ -35,30 +35,45 @@ struct AttnParams {
     float scale_log2;     // (1/sqrt(64)) * log2(e)
 };
 
-// One streaming pass over a score tile: p = 2^(s*c - m_ref*c), row sum, tile max; P written to TMEM as packed bf16.
+// 32 (or, for a tail chunk, 16) scores -> p = 2^(s*c - m_ref*c) -> packed bf16 in TMEM; accumulates the row sum / tile max
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], bool wide, uint32_t tP_col, float c, float mc,
+                                              float& acc, float& mt) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float e0 = 0.f, e1 = 0.f;
+        if (wide || i < 8) {
+            const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
+            mt = fmax3(mt, s0, s1);
+            e0 = ex2_approx(fmaf(s0, c, -mc));
+            e1 = ex2_approx(fmaf(s1, c, -mc));
+        }
+        acc += e0 + e1;
+        pk[i] = pack_bf16(e0, e1);
+    }
+    tmem_st16(tP_col, pk);                     // a 16-column tail chunk stores 8 meaningful + 8 zero words (never read)
+}
+
+// One streaming pass over a score tile.  The TMEM load of chunk i+1 is in flight while chunk i is exponentiated
+// (two register buffers; a buffer is only read after the tcgen05.wait::ld that follows its load).
 __device__ __forceinline__ void softmax_pass(uint32_t tS, uint32_t tP, int nk, float c, float mc, float& acc, float& mt) {
     acc = 0.f;
     mt = -INFINITY;
-#pragma unroll 1
-    for (int col = 0; col < nk; col += 32) {
-        uint32_t r[32];
-        const bool wide = col + 32 <= nk;
-        if (wide) tmem_ld32(tS + col, r); else tmem_ld16(tS + col, r);
-        tmem_wait_ld();
-        uint32_t pk[16];
+    uint32_t ra[32], rb[32];
+    if (nk >= 32) tmem_ld32(tS, ra); else tmem_ld16(tS, ra);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float e0 = 0.f, e1 = 0.f;
-            if (wide || i < 8) {
-                const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
-                mt = fmaxf(mt, fmaxf(s0, s1));
-                e0 = ex2_approx(fmaf(s0, c, -mc));
-                e1 = ex2_approx(fmaf(s1, c, -mc));
+    for (int ci = 0; ci < ATT_TILE / 32; ++ci) {
+        const int col = ci * 32;
+        if (col < nk) {
+            tmem_wait_ld();
+            const int nxt = col + 32;
+            if (nxt < nk) {
+                if ((ci & 1) == 0) { if (nxt + 32 <= nk) tmem_ld32(tS + nxt, rb); else tmem_ld16(tS + nxt, rb); }
+                else               { if (nxt + 32 <= nk) tmem_ld32(tS + nxt, ra); else tmem_ld16(tS + nxt, ra); }
             }
-            acc += e0 + e1;
-            pk[i] = pack_bf16(e0, e1);
+            if ((ci & 1) == 0) softmax_chunk(ra, col + 32 <= nk, tP + col / 2, c, mc, acc, mt);
+            else               softmax_chunk(rb, col + 32 <= nk, tP + col / 2, c, mc, acc, mt);
         }
-        tmem_st16(tP + col / 2, pk);           // a 16-column tail chunk stores 8 meaningful + 8 zero words (never read)
     }
 }
 

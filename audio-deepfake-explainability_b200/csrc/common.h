@@ -36,6 +36,9 @@ int set_error(int code, const char* fmt, ...);
 // bf16 tensor map, up to 3 dims (dim0 innermost), 128-byte swizzle, OOB reads filled with zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// general form: elem_bytes 2 (bf16) or 4 (fp32); swizzle128 = 0 -> dense (un-swizzled) shared-memory box
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -1,13 +1,15 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] . W[N,K]^T  (+ fused epilogue)
 //
-//   warp 0 : TMA producer (cp.async.bulk.tensor, 128B swizzle, 3/4-stage mbarrier ring)
-//   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate in TMEM)
-//   warps 2-9 : epilogue (tcgen05.ld -> registers -> smem transpose -> fused bias / GELU / positional-encoding /
-//               residual on coalesced rows -> global); with K = 384 the epilogue is as long as the MMAs, so it gets
-//               8 warps and batched (unrolled) global accesses
-//
-// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.  Used for every dense
-// contraction of the SpecTTTra forward (tokenizer projections, QKV, attention projection, MLP).
+//   warp 0    : TMA producer (cp.async.bulk.tensor, 128B swizzle, 3-stage mbarrier ring)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate in TMEM)
+//   warps 2-9 : epilogue.  TMEM lane == tile row, so tcgen05.ld hands every thread one row of the accumulator.
+//               bf16 / residual outputs: bias (+GELU) in registers, pack, st.shared into a 128B-swizzled per-warp slab
+//               and ONE TMA tensor store per 32-row x 128-byte slab - a plain store for bf16 outputs, a TMA reduce-add
+//               (x += acc + bias performed in L2) for the fp32 residual stream, which therefore is never loaded.
+//               token-mode outputs (tokenizer: row remap + positional encoding) take a generic coalescing path.
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.  With K = 384 the epilogue is as
+// long as the MMAs, hence eight epilogue warps (two per TMEM lane quarter, splitting the column groups).
+// Used for every dense contraction of the SpecTTTra forward (tokenizer projections, QKV, attention projection, MLP).
 #include "common.h"
 #include "ptx.cuh"
 
@@ -15,8 +17,11 @@ namespace b200x {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;      // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_EPI_WARPS = 8;                       // two warps per TMEM lane quarter (they split the columns)
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_SLAB_BYTES = 32 * 128;             // 32 rows x 128 bytes
+constexpr int GEMM_EPI_WARP_BYTES = 2 * GEMM_SLAB_BYTES + 1024;   // double-buffered slab (+ spare for the token path)
 
 struct GemmParams {
     int M, N, K;
@@ -25,94 +30,62 @@ struct GemmParams {
     int out_mode;         // B200X_GEMM_OUT_*
     const float* bias;    // [N] or null
     int act_gelu;
-    const float* resid;   // fp32 [.., ldc] (OUT_F32_RESID), may alias out
     const float* pe;      // fp32 [group_in, N] (OUT_F32_TOKEN) or null
     int group_in, group_out, group_off;   // out_row = (m / group_in) * group_out + group_off + m % group_in
 };
 
 template <int BN>
 struct GemmSmem {
-    static constexpr int STAGES = BN > 208 ? 3 : 4;
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;               // per epilogue warp: [32 rows][36 floats]
-    static constexpr int EPI_BYTES = GEMM_EPI_WARPS * 32 * 36 * 4;
+    static constexpr int EPI_OFFSET = GEMM_STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = GEMM_EPI_WARPS * GEMM_EPI_WARP_BYTES;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
     static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
+    static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
-// One staged chunk of CW columns: the warp's 32 rows sit in `stage` (row stride CW + 4 floats); a group of CW/4 lanes
-// covers one row with float4s.  All shared / global loads of the chunk are issued before any of them is consumed.
+// Generic (token-mode) chunk: the warp's 32 rows x CW columns sit in `stage` (row stride CW + 4 floats); a group of CW/4
+// lanes covers one row with float4s so global accesses are row-contiguous.
 template <int CW>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* stage, int lane, int m_warp, int n_base) {
+__device__ __forceinline__ void epilogue_chunk_generic(const GemmParams& p, const float* stage, int lane, int m_warp, int n_base) {
     constexpr int LD = CW + 4, LPR = CW / 4, RPI = 32 / LPR, NIT = 32 / RPI;
     const int col = (lane % LPR) * 4;
     const int n0 = n_base + col;
     if (n0 >= p.N) return;
-    float4 v[NIT];
-    int orow[NIT];
-    int gidx[NIT];
-    bool okr[NIT];
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        const int row = it * RPI + lane / LPR;
-        const int m = m_warp + row;
-        okr[it] = m < p.M;
-        v[it] = *reinterpret_cast<const float4*>(stage + row * LD + col);
-        orow[it] = m;
-        gidx[it] = 0;
-        if (p.group_in > 0) {
-            gidx[it] = m % p.group_in;
-            orow[it] = (m / p.group_in) * p.group_out + p.group_off + gidx[it];
-        }
-    }
-    float4 add[NIT];
-    const bool has_add = (p.out_mode == B200X_GEMM_OUT_F32_RESID) || (p.out_mode == B200X_GEMM_OUT_F32_TOKEN && p.pe != nullptr);
-    if (has_add) {
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            add[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (okr[it]) {
-                const float* src = (p.out_mode == B200X_GEMM_OUT_F32_RESID) ? p.resid + static_cast<long long>(orow[it]) * p.ldc + n0
-                                                                           : p.pe + static_cast<long long>(gidx[it]) * p.N + n0;
-                add[it] = *reinterpret_cast<const float4*>(src);
-            }
-        }
-    }
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias != nullptr) bias4 = *reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
-        float4 x = v[it];
+        const int row = it * RPI + lane / LPR;
+        const int m = m_warp + row;
+        if (m >= p.M) continue;
+        float4 x = *reinterpret_cast<const float4*>(stage + row * LD + col);
         x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
         if (p.act_gelu) { x.x = gelu_fast(x.x); x.y = gelu_fast(x.y); x.z = gelu_fast(x.z); x.w = gelu_fast(x.w); }
-        if (has_add) { x.x += add[it].x; x.y += add[it].y; x.z += add[it].z; x.w += add[it].w; }
-        v[it] = x;
-    }
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        if (!okr[it]) continue;
-        if (p.out_mode == B200X_GEMM_OUT_BF16) {
-            uint2 w;
-            w.x = pack_bf16(v[it].x, v[it].y);
-            w.y = pack_bf16(v[it].z, v[it].w);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(orow[it]) * p.ldc + n0) = w;
-        } else {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(orow[it]) * p.ldc + n0) = v[it];
+        int orow = m, gidx = 0;
+        if (p.group_in > 0) {
+            gidx = m % p.group_in;
+            orow = (m / p.group_in) * p.group_out + p.group_off + gidx;
         }
+        if (p.pe != nullptr) {
+            const float4 a = *reinterpret_cast<const float4*>(p.pe + static_cast<long long>(gidx) * p.N + n0);
+            x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+        }
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(orow) * p.ldc + n0) = x;
     }
 }
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCtail, GemmParams p) {
     using L = GemmSmem<BN>;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int GEMM_STAGES = L::STAGES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + GEMM_STAGES;
     uint64_t* tfull_bar = empty_bar + GEMM_STAGES;
@@ -129,6 +102,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
         for (int s = 0; s < GEMM_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -194,47 +168,139 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9)
-        // TMEM lane == tile row, so tcgen05.ld hands every thread one row.  Each 32-column chunk is transposed through a
-        // padded, warp-private shared-memory tile so that global traffic is row-contiguous; two warps per lane quarter and
-        // fully unrolled (batched) shared / global accesses keep enough requests in flight to hide their latency.
         const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter + 32)
         const int half = (warp - 2) >> 2;                // which of the two warps sharing this lane quarter
-        float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + (warp - 2) * (32 * 36);
-        constexpr int NCHUNK = (BN + 31) / 32;
+        uint8_t* slab = smem + L::EPI_OFFSET + (warp - 2) * GEMM_EPI_WARP_BYTES;
+        int buf = 0;
         int as = 0;
         uint32_t aphase = 0;
+        const int sw = lane & 7;                         // 128B-swizzle phase of this thread's slab row
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const int m_warp = m_blk * GEMM_BM + quarter * 32;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+            if (p.out_mode == B200X_GEMM_OUT_BF16) {
+                // column groups of 64 (one 128-byte bf16 row per thread); BN = 208 ends with a 16-column group
+                constexpr int NG = (BN + 63) / 64;
 #pragma unroll 1
-            for (int ci = half; ci < NCHUNK; ci += 2) {
-                const int c = ci * 32;
-                const bool wide = (c + 32 <= BN);        // BN = 208 ends with a 16-column chunk
-                uint32_t r[32];
-                if (wide) tmem_ld32(t_row + c, r); else tmem_ld16(t_row + c, r);
-                tmem_wait_ld();
-                if (wide) {
+                for (int g = half; g < NG; g += 2) {
+                    const int c = g * 64;
+                    const int n0 = n_blk * BN + c;
+                    const bool full = (c + 64 <= BN);
+                    if (lane == 0) bulk_wait_read<1>();          // the store that last used this buffer has read it
+                    __syncwarp();
+                    uint8_t* dst = slab + buf * GEMM_SLAB_BYTES;
+                    if (full) {
+                        uint32_t r[64];
+                        tmem_ld32(t_row + c, r);
+                        tmem_ld32(t_row + c + 32, r + 32);
+                        tmem_wait_ld();
+                        uint32_t w[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<uint4*>(stage + lane * 36 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-                } else {
+                        for (int i = 0; i < 64; i += 4) {
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                            float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
+                            float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
+                            if (p.act_gelu) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3); }
+                            w[i / 2] = pack_bf16(v0, v1);
+                            w[i / 2 + 1] = pack_bf16(v2, v3);
+                        }
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        *reinterpret_cast<uint4*>(stage + lane * 20 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) =
+                                make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+                    } else {
+                        uint32_t r[16];
+                        tmem_ld16(t_row + c, r);
+                        tmem_wait_ld();
+                        uint32_t w[8];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                            float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
+                            float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
+                            if (p.act_gelu) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3); }
+                            w[i / 2] = pack_bf16(v0, v1);
+                            w[i / 2 + 1] = pack_bf16(v2, v3);
+                        }
+                        *reinterpret_cast<uint4*>(dst + lane * 32) = make_uint4(w[0], w[1], w[2], w[3]);       // dense 32-byte rows
+                        *reinterpret_cast<uint4*>(dst + lane * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && m_warp < p.M && n0 < p.N) {
+                        tma_store_2d(full ? &tmC : &tmCtail, dst, n0, m_warp);   // rows >= M / cols >= N are clipped by TMA
+                        bulk_commit();
+                    }
+                    buf ^= 1;
                 }
+            } else if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
+                // column groups of 32 fp32 (128 bytes per thread row); x += acc + bias via TMA reduce-add
+                constexpr int NG = BN / 32;
+#pragma unroll 1
+                for (int g = half; g < NG; g += 2) {
+                    const int c = g * 32;
+                    const int n0 = n_blk * BN + c;
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+                    uint8_t* dst = slab + buf * GEMM_SLAB_BYTES;
+                    uint32_t r[32];
+                    tmem_ld32(t_row + c, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias != nullptr && n0 + 4 * j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * j));
+                        const float4 v = make_float4(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y,
+                                                     __uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
+                        *reinterpret_cast<float4*>(dst + lane * 128 + ((j ^ sw) << 4)) = v;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && m_warp < p.M && n0 < p.N) {
+                        tma_reduce_add_2d(&tmC, dst, n0, m_warp);
+                        bulk_commit();
+                    }
+                    buf ^= 1;
+                }
+            } else {
+                // token mode: generic transposing path (row remap + positional encoding), 32-column chunks
+                float* stage = reinterpret_cast<float*>(slab);
+                if (lane == 0) bulk_wait_read<0>();
                 __syncwarp();
-                if (wide) epilogue_chunk<32>(p, stage, lane, m_warp, n_blk * BN + c);
-                else epilogue_chunk<16>(p, stage, lane, m_warp, n_blk * BN + c);
-                __syncwarp();
+                constexpr int NCHUNK = (BN + 31) / 32;
+#pragma unroll 1
+                for (int ci = half; ci < NCHUNK; ci += 2) {
+                    const int c = ci * 32;
+                    const bool wide = (c + 32 <= BN);
+                    uint32_t r[32];
+                    if (wide) tmem_ld32(t_row + c, r); else tmem_ld16(t_row + c, r);
+                    tmem_wait_ld();
+                    if (wide) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<uint4*>(stage + lane * 36 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<uint4*>(stage + lane * 20 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                    }
+                    __syncwarp();
+                    if (wide) epilogue_chunk_generic<32>(p, stage, lane, m_warp, n_blk * BN + c);
+                    else epilogue_chunk_generic<16>(p, stage, lane, m_warp, n_blk * BN + c);
+                    __syncwarp();
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (lane == 0) bulk_wait<0>();                   // all tensor stores of this warp have completed
     }
 
     tc_fence_before();
@@ -245,7 +311,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 static int g_num_sms = 0;
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
+                       const GemmParams& p, cudaStream_t stream) {
     using L = GemmSmem<BN>;
     static bool configured = false;
     if (!configured) {
@@ -259,7 +326,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     const int tiles = ceil_div(p.M, GEMM_BM) * ceil_div(p.N, BN);
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_bf16_tn_kernel<BN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+    gemm_bf16_tn_kernel<BN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmCtail, p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }
@@ -277,9 +344,12 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
     B200X_REQUIRE(d_bias == nullptr || (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0, "gemm: bias not 16-byte aligned");
     B200X_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "gemm: lda=%d / ldw=%d must be multiples of 8 (16-byte rows)", lda, ldw);
     B200X_REQUIRE(out_mode >= B200X_GEMM_OUT_BF16 && out_mode <= B200X_GEMM_OUT_F32_TOKEN, "gemm: bad out_mode %d", out_mode);
-    B200X_REQUIRE(out_mode != B200X_GEMM_OUT_F32_RESID || d_resid != nullptr, "gemm: residual pointer missing");
+    B200X_REQUIRE(out_mode != B200X_GEMM_OUT_F32_RESID || (d_resid != nullptr && d_resid == d_out),
+                  "gemm: the residual epilogue accumulates in place (TMA reduce-add): d_resid must equal d_out");
+    B200X_REQUIRE(out_mode != B200X_GEMM_OUT_F32_RESID || act_gelu == 0, "gemm: GELU is not available with the residual epilogue");
     B200X_REQUIRE(ldc % (out_mode == B200X_GEMM_OUT_BF16 ? 8 : 4) == 0, "gemm: ldc=%d not 16-byte aligned", ldc);
-    CUtensorMap tmA, tmB;
+    B200X_REQUIRE(out_mode != B200X_GEMM_OUT_F32_RESID || block_n % 32 == 0, "gemm: residual epilogue needs block_n %% 32 == 0");
+    CUtensorMap tmA, tmB, tmC, tmCtail;
     const uint64_t da[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     const uint64_t sa[1] = {static_cast<uint64_t>(lda) * 2};
     const uint32_t ba[2] = {GEMM_BK, GEMM_BM};
@@ -288,13 +358,29 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
     const uint64_t sw[1] = {static_cast<uint64_t>(ldw) * 2};
     const uint32_t bw[2] = {GEMM_BK, static_cast<uint32_t>(block_n)};
     B200X_TRY(make_tmap_bf16(&tmB, d_w, 2, dw, sw, bw));
-    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_resid, d_pe, group_in, group_out, group_off};
+    // output maps: 32-row slabs, 128 bytes wide (64 bf16 / 32 fp32), plus a dense 16-column bf16 tail map
+    const uint64_t dc[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    if (out_mode == B200X_GEMM_OUT_F32_RESID) {
+        const uint64_t sc[1] = {static_cast<uint64_t>(ldc) * 4};
+        const uint32_t bc[2] = {32, 32};
+        B200X_TRY(make_tmap(&tmC, d_out, 4, 2, dc, sc, bc, 1));
+        tmCtail = tmC;
+    } else if (out_mode == B200X_GEMM_OUT_BF16) {
+        const uint64_t sc[1] = {static_cast<uint64_t>(ldc) * 2};
+        const uint32_t bc[2] = {64, 32}, bt[2] = {16, 32};
+        B200X_TRY(make_tmap(&tmC, d_out, 2, 2, dc, sc, bc, 1));
+        B200X_TRY(make_tmap(&tmCtail, d_out, 2, 2, dc, sc, bt, 0));
+    } else {
+        tmC = tmA;            // unused in token mode
+        tmCtail = tmA;
+    }
+    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (block_n) {
-        case 128: return launch_gemm<128>(tmA, tmB, p, s);
-        case 192: return launch_gemm<192>(tmA, tmB, p, s);
-        case 208: return launch_gemm<208>(tmA, tmB, p, s);
-        case 256: return launch_gemm<256>(tmA, tmB, p, s);
+        case 128: return launch_gemm<128>(tmA, tmB, tmC, tmCtail, p, s);
+        case 192: return launch_gemm<192>(tmA, tmB, tmC, tmCtail, p, s);
+        case 208: return launch_gemm<208>(tmA, tmB, tmC, tmCtail, p, s);
+        case 256: return launch_gemm<256>(tmA, tmB, tmC, tmCtail, p, s);
         default: return set_error(B200X_ERR_INVALID, "gemm: unsupported block_n %d (128/192/208/256)", block_n);
     }
 }

@@ -19,8 +19,13 @@ dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
 
 
+ITERS = int(os.environ.get("KB_ITERS", "0"))
+WARMUP = int(os.environ.get("KB_WARMUP", "3"))
+
+
 def timeit(fn, flops=None, bytes_=None, name="", iters=20):
-    for _ in range(3):
+    iters = ITERS or iters
+    for _ in range(WARMUP):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
