@@ -38,12 +38,14 @@ SIGNATURES = {
     "b200x_set_device": (C.c_int, [C.c_int]),
     "b200x_device_count": (C.c_int, [c_i32p]),
     "b200x_stft": (C.c_int, [VP, C.c_int64, C.c_int, C.c_int, C.c_int, VP, C.c_int, VP]),
-    "b200x_istft_masked": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_float, VP, VP, C.c_int64, VP, VP]),
+    "b200x_istft_masked": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_float, VP, VP, C.c_int64, VP, VP, C.c_int, VP]),
+    "b200x_frame_ranges": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),
+    "b200x_mel_base_maxima": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP]),
     "b200x_mel_frames_per_cta": (C.c_int, []),
     "b200x_mel_db": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
-                               VP, C.c_double, C.c_int64, VP, VP, VP]),
-    "b200x_mel_normalize_resize": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float,
-                                             C.c_int, VP, VP, VP, VP, C.c_int, VP]),
+                               VP, C.c_double, C.c_int64, VP, C.c_int, VP, VP, C.c_int, VP]),
+    "b200x_mel_normalize_resize": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                             C.c_float, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, VP]),
     "b200x_mix_stems": (C.c_int, [VP, C.c_int64, C.c_int, VP, C.c_int, VP, C.c_int64, VP]),
     "b200x_gemm_bf16": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_int, C.c_int,
                                   VP, C.c_int, VP, VP, C.c_int, C.c_int, C.c_int, VP]),

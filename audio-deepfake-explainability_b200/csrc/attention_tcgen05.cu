@@ -35,21 +35,24 @@ struct AttnParams {
     float scale_log2;     // (1/sqrt(64)) * log2(e)
 };
 
-// 32 (or, for a tail chunk, 16) scores -> p = 2^(s*c - m_ref*c) -> packed bf16 in TMEM; accumulates the row sum / tile max
+// 32 (or, for a tail chunk, 16) scores -> p = 2^(s*c - m_ref*c) -> packed bf16 in TMEM; accumulates the row sum / tile max.
+// The fp32 -> bf16 conversion is a byte permute that keeps the high halves (truncation) instead of F2FP: the conversion
+// unit shares the MUFU pipe, which is what bounds this kernel.  The row sum is taken over the TRUNCATED values, so the
+// softmax weights stay exactly normalised and carry the same error variance as round-to-nearest, without bias.
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], bool wide, uint32_t tP_col, float c, float mc,
                                               float& acc, float& mt) {
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        float e0 = 0.f, e1 = 0.f;
+        uint32_t b0 = 0u, b1 = 0u;
         if (wide || i < 8) {
             const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
             mt = fmax3(mt, s0, s1);
-            e0 = ex2_approx(fmaf(s0, c, -mc));
-            e1 = ex2_approx(fmaf(s1, c, -mc));
+            b0 = __float_as_uint(ex2_approx(fmaf(s0, c, -mc))) & 0xFFFF0000u;
+            b1 = __float_as_uint(ex2_approx(fmaf(s1, c, -mc))) & 0xFFFF0000u;
         }
-        acc += e0 + e1;
-        pk[i] = pack_bf16(e0, e1);
+        acc += __uint_as_float(b0) + __uint_as_float(b1);
+        pk[i] = __byte_perm(b0, b1, 0x7632);      // low half = bf16(s0), high half = bf16(s1)
     }
     tmem_st16(tP_col, pk);                     // a 16-column tail chunk stores 8 meaningful + 8 zero words (never read)
 }

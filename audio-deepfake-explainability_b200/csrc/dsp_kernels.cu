@@ -127,6 +127,8 @@ struct IstftParams {
     int mode;                 // 0 none, 1 occlusion rectangle, 2 per-bin gain, 3 keep only the rectangle
     int hops_per_strip;
     double* sumsq;            // optional [copies]: sum of squares of the written samples (for RMS matching)
+    const int* frame_range;   // optional [copies][2]: classifier frames [ma, mb) that differ from the unperturbed track;
+                              // only the samples those frames read are synthesised (iSTFT linearity)
 };
 
 __global__ void __launch_bounds__(DSP_THREADS)
@@ -136,9 +138,16 @@ istft_masked_kernel(IstftParams p) {
     float2* tile = dsp_smem + warp * FFT_TILE;
     const int copy = blockIdx.y;
     const int strip = blockIdx.x * DSP_WARPS + warp;
-    // padded hops [hp_a, hp_b) of this strip; valid output hops are 2 .. n_frames
-    const int hp_a = 2 + strip * p.hops_per_strip;
-    const int hp_b = min(hp_a + p.hops_per_strip, p.n_frames + 1);
+    // padded hops [hp_a, hp_b) of this strip; valid output hops are 2 .. n_frames (restricted to what frames [ma, mb) read)
+    int h_lo = 2, h_hi = p.n_frames;
+    if (p.frame_range != nullptr) {
+        const int ma = p.frame_range[2 * copy], mb = p.frame_range[2 * copy + 1];
+        if (mb <= ma) return;
+        h_lo = max(2, ma);
+        h_hi = min(p.n_frames, mb + 2);
+    }
+    const int hp_a = h_lo + strip * p.hops_per_strip;
+    const int hp_b = min(hp_a + p.hops_per_strip, h_hi + 1);
     if (hp_a >= hp_b) return;
     int t0 = 0, t1 = 0, f0 = 0, f1 = 0;
     if (p.mode == 1 || p.mode == 3) {
@@ -250,9 +259,11 @@ struct MelParams {
     const int* fb_offset;      // [n_mels] offset into fb_weights
     const float* fb_weights;
     float amin;
-    float* db;                 // [copies][n_frames][n_mels]
+    float* db;                 // [copies][db_frames][n_mels]; row (t - ma) when frame_range is given
     float* cta_max;            // [copies][gridDim.x]
     int frames_per_cta;
+    int db_frames;             // frame capacity per copy of db
+    const int* frame_range;    // optional [copies][2] = [ma, mb): only these frames are computed
 };
 
 __global__ void __launch_bounds__(DSP_THREADS)
@@ -270,8 +281,10 @@ mel_db_kernel(MelParams p) {
         if (!(r_x < 1e-8)) gain = static_cast<float>(p.ref_rms / r_x);
     }
     float vmax = -INFINITY;
-    const int f_begin = blockIdx.x * p.frames_per_cta;
-    const int f_end = min(f_begin + p.frames_per_cta, p.n_frames);
+    int f_lo = 0, f_hi = p.n_frames;
+    if (p.frame_range != nullptr) { f_lo = p.frame_range[2 * copy]; f_hi = p.frame_range[2 * copy + 1]; }
+    const int f_begin = f_lo + blockIdx.x * p.frames_per_cta;
+    const int f_end = min(f_begin + p.frames_per_cta, f_hi);
     for (int t = f_begin + warp; t < f_end; t += DSP_WARPS) {
         const long long base = static_cast<long long>(t) * HOP - NFFT / 2;
         float2 v[32];
@@ -300,7 +313,7 @@ mel_db_kernel(MelParams p) {
         for (int r = 0; r < 32; ++r) pw[lane + 32 * r] = X[r].x * X[r].x + X[r].y * X[r].y;
         if (lane == 0) pw[1024] = xn.x * xn.x;
         __syncwarp();
-        float* out = p.db + (static_cast<long long>(copy) * p.n_frames + t) * p.n_mels;
+        float* out = p.db + (static_cast<long long>(copy) * p.db_frames + (t - f_lo)) * p.n_mels;
         for (int f = lane; f < p.n_mels; f += 32) {
             const int st = __ldg(&p.fb_start[f]), cnt = __ldg(&p.fb_count[f]);
             const float* w = p.fb_weights + __ldg(&p.fb_offset[f]);
@@ -323,26 +336,57 @@ mel_db_kernel(MelParams p) {
     }
 }
 
+// Where a copy's dB rows live: frames [ma, mb) in its own compact buffer, every other frame in the track's baseline
+// (those frames are bit-identical to the unperturbed track, so they are computed once per track).
+struct DbView {
+    const float* own;          // [db_frames][n_mels] of this copy
+    const float* base;         // [n_frames][n_mels] baseline or nullptr
+    int ma, mb, n_mels;
+    __device__ __forceinline__ const float* row(int t) const {
+        return (base == nullptr || (t >= ma && t < mb)) ? own + static_cast<long long>(t - ma) * n_mels
+                                                        : base + static_cast<long long>(t) * n_mels;
+    }
+};
+
+struct StatsParams {
+    const float* db;           // [copies][db_frames][n_mels]
+    int db_frames, n_frames, n_mels;
+    const float* cta_max;
+    int n_cta_max;
+    float top_db;
+    const float* base;         // optional baseline dB [n_frames][n_mels]
+    const float* base_premax;  // [n_frames + 1]: max over baseline frames < m
+    const float* base_sufmax;  // [n_frames + 1]: max over baseline frames >= m
+    const int* frame_range;    // [copies][2] (required when base != nullptr)
+    double2* partial;
+    float* floor_out;
+};
+
 // clamp at (max - top_db) and reduce sum / sum of squares: partial[copy][block] = (sum, sumsq), fp64
 __global__ void __launch_bounds__(256)
-mel_stats_kernel(const float* __restrict__ db, long long per_copy, const float* __restrict__ cta_max, int n_cta_max,
-                 float top_db, double2* __restrict__ partial, float* __restrict__ floor_out) {
+mel_stats_kernel(StatsParams p) {
     __shared__ float s_floor;
     __shared__ double s_a[8], s_b[8];
     const int copy = blockIdx.y;
+    DbView v;
+    v.own = p.db + static_cast<long long>(copy) * p.db_frames * p.n_mels;
+    v.base = p.base; v.n_mels = p.n_mels; v.ma = 0; v.mb = p.n_frames;
+    if (p.base != nullptr) { v.ma = p.frame_range[2 * copy]; v.mb = p.frame_range[2 * copy + 1]; }
     if (threadIdx.x == 0) {
         float m = -INFINITY;
-        for (int i = 0; i < n_cta_max; ++i) m = fmaxf(m, cta_max[static_cast<long long>(copy) * n_cta_max + i]);
-        s_floor = m - top_db;
-        if (blockIdx.x == 0) floor_out[copy] = s_floor;
+        for (int i = 0; i < p.n_cta_max; ++i) m = fmaxf(m, p.cta_max[static_cast<long long>(copy) * p.n_cta_max + i]);
+        if (p.base != nullptr) m = fmaxf(m, fmaxf(p.base_premax[v.ma], p.base_sufmax[v.mb]));
+        s_floor = m - p.top_db;
+        if (blockIdx.x == 0) p.floor_out[copy] = s_floor;
     }
     __syncthreads();
     const float fl = s_floor;
-    const float4* src = reinterpret_cast<const float4*>(db + static_cast<long long>(copy) * per_copy);
-    const long long n4 = per_copy / 4;
+    const int per_row4 = p.n_mels / 4;
+    const long long n4 = static_cast<long long>(p.n_frames) * per_row4;
     double a = 0.0, b = 0.0;
     for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float4 x = src[i];
+        const int t = static_cast<int>(i / per_row4), c4 = static_cast<int>(i % per_row4);
+        const float4 x = reinterpret_cast<const float4*>(v.row(t))[c4];
         const float v0 = fmaxf(x.x, fl), v1 = fmaxf(x.y, fl), v2 = fmaxf(x.z, fl), v3 = fmaxf(x.w, fl);
         a += static_cast<double>(v0) + v1 + v2 + v3;
         b += static_cast<double>(v0) * v0 + static_cast<double>(v1) * v1 + static_cast<double>(v2) * v2 +
@@ -358,14 +402,17 @@ mel_stats_kernel(const float* __restrict__ db, long long per_copy, const float* 
     if (threadIdx.x == 0) {
         double sa = 0.0, sb = 0.0;
         for (int i = 0; i < 8; ++i) { sa += s_a[i]; sb += s_b[i]; }
-        partial[static_cast<long long>(copy) * gridDim.x + blockIdx.x] = make_double2(sa, sb);
+        p.partial[static_cast<long long>(copy) * gridDim.x + blockIdx.x] = make_double2(sa, sb);
     }
 }
 
 // normalise + bilinear resize along time (F.interpolate(mode='bilinear', align_corners=False); the mel axis keeps its
 // size so its weights are exactly (1, 0)) -> bf16 in [time][mel] (temporal tokenizer operand) and [mel][time] (spectral)
 struct ResizeParams {
-    const float* db;           // [copies][n_frames][n_mels]
+    const float* db;           // [copies][db_frames][n_mels]
+    int db_frames;
+    const float* base;         // optional baseline dB
+    const int* frame_range;
     const double2* partial;
     const float* floor_val;
     int n_partial;
@@ -397,7 +444,10 @@ mel_resize_kernel(ResizeParams p) {
     __syncthreads();
     const float mean = s_mean, inv = s_inv, fl = p.floor_val[copy];
     const float scale = static_cast<float>(p.n_frames) / static_cast<float>(p.out_t);
-    const float* db = p.db + static_cast<long long>(copy) * p.n_frames * p.n_mels;
+    DbView v;
+    v.own = p.db + static_cast<long long>(copy) * p.db_frames * p.n_mels;
+    v.base = p.base; v.n_mels = p.n_mels; v.ma = 0; v.mb = p.n_frames;
+    if (p.base != nullptr) { v.ma = p.frame_range[2 * copy]; v.mb = p.frame_range[2 * copy + 1]; }
     const int j0 = blockIdx.x * 64;
     for (int idx = threadIdx.x; idx < 64 * p.n_mels; idx += blockDim.x) {
         const int jj = idx / p.n_mels, f = idx % p.n_mels;
@@ -408,8 +458,8 @@ mel_resize_kernel(ResizeParams p) {
         const int i0 = static_cast<int>(src);
         const int i1 = i0 + (i0 < p.n_frames - 1 ? 1 : 0);
         const float lam1 = src - static_cast<float>(i0), lam0 = 1.0f - lam1;
-        const float x0 = (fmaxf(db[static_cast<long long>(i0) * p.n_mels + f], fl) - mean) * inv;
-        const float x1 = (fmaxf(db[static_cast<long long>(i1) * p.n_mels + f], fl) - mean) * inv;
+        const float x0 = (fmaxf(v.row(i0)[f], fl) - mean) * inv;
+        const float x1 = (fmaxf(v.row(i1)[f], fl) - mean) * inv;
         const __nv_bfloat16 o = __float2bfloat16_rn(lam0 * x0 + lam1 * x1);
         p.img_t[(static_cast<long long>(copy) * p.out_t + j) * p.n_mels + f] = o;
         s_tile[jj][f] = o;
@@ -419,6 +469,39 @@ mel_resize_kernel(ResizeParams p) {
         const int f = idx / 64, jj = idx % 64;
         const int j = j0 + jj;
         if (j < p.out_t) p.img_f[(static_cast<long long>(copy) * p.n_mels + f) * p.ld_f + j] = s_tile[jj][f];
+    }
+}
+
+// classifier frames touched by an occlusion window: a patch on STFT frames [t0, t1) changes samples
+// [t0*hop - n_fft/2, (t1-1)*hop + n_fft/2), i.e. classifier (hop 512, n_fft 2048) frames [t0 - 3, t1 + 3); one more
+// frame on each side covers the sample that the first / last frame reaches through reflect padding
+__global__ void frame_ranges_kernel(const int* __restrict__ windows, int n, int n_frames, int* __restrict__ ranges) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t0 = windows[4 * i], t1 = windows[4 * i + 1], f0 = windows[4 * i + 2], f1 = windows[4 * i + 3];
+    int ma = 0, mb = 0;
+    if (t1 > t0 && f1 > f0) { ma = max(t0 - 4, 0); mb = min(t1 + 4, n_frames); }
+    ranges[2 * i] = ma;
+    ranges[2 * i + 1] = mb;
+}
+
+// pre[m] = max over baseline frames < m, suf[m] = max over frames >= m  (m = 0 .. n_frames); one block
+__global__ void base_maxima_kernel(const float* __restrict__ db, int n_frames, int n_mels, float* __restrict__ pre,
+                                   float* __restrict__ suf) {
+    extern __shared__ float s_fm[];                 // per-frame maxima
+    for (int t = threadIdx.x; t < n_frames; t += blockDim.x) {
+        float m = -INFINITY;
+        for (int f = 0; f < n_mels; ++f) m = fmaxf(m, db[static_cast<long long>(t) * n_mels + f]);
+        s_fm[t] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = -INFINITY;
+        for (int t = 0; t <= n_frames; ++t) { pre[t] = m; if (t < n_frames) m = fmaxf(m, s_fm[t]); }
+    } else if (threadIdx.x == 32) {
+        float m = -INFINITY;
+        suf[n_frames] = m;
+        for (int t = n_frames - 1; t >= 0; --t) { m = fmaxf(m, s_fm[t]); suf[t] = m; }
     }
 }
 
@@ -455,7 +538,8 @@ extern "C" int b200x_stft(const float* d_wave, int64_t n_samples, int n_fft, int
 
 extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_frames, int copies, int mode,
                                   const int32_t* d_windows, float occlusion_value, const float* d_gains, float* d_y,
-                                  int64_t y_stride, double* d_sumsq, void* stream) {
+                                  int64_t y_stride, double* d_sumsq, const int32_t* d_frame_range, int max_range_frames,
+                                  void* stream) {
     B200X_REQUIRE(mode >= 0 && mode <= 3, "istft: bad mode %d", mode);
     B200X_REQUIRE((mode != 1 && mode != 3) || d_windows != nullptr, "istft: windows missing");
     B200X_REQUIRE(mode != 2 || d_gains != nullptr, "istft: gains missing");
@@ -468,9 +552,14 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
     p.S = reinterpret_cast<const float2*>(d_spec); p.stride = spec_stride; p.n_frames = n_frames;
     p.out_len = static_cast<long long>(HOP) * (n_frames - 1); p.out_stride = y_stride; p.y = d_y;
     p.windows = d_windows; p.occlusion_value = occlusion_value; p.gains = d_gains; p.mode = mode;
-    p.hops_per_strip = 29; p.sumsq = d_sumsq;
+    p.sumsq = d_sumsq; p.frame_range = d_frame_range;
     B200X_REQUIRE(y_stride >= p.out_len, "istft: y_stride too small");
-    const int strips = ceil_div(n_frames - 1, p.hops_per_strip);
+    B200X_REQUIRE(d_frame_range == nullptr || d_sumsq == nullptr, "istft: sum of squares needs the full signal");
+    // hops to synthesise per copy: everything, or what the affected classifier frames read (range + 3 hops)
+    const int hops = d_frame_range ? std::min(n_frames - 1, std::max(1, max_range_frames) + 3) : n_frames - 1;
+    // shorter strips when there is little work per copy, so that the launch still fills the SMs (3 warm-up frames/strip)
+    p.hops_per_strip = (static_cast<long long>(copies) * hops >= 30000) ? 29 : 13;
+    const int strips = ceil_div(hops, p.hops_per_strip);
     dim3 grid(ceil_div(strips, DSP_WARPS), copies);
     istft_masked_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(p);
     B200X_CUDA_TRY(cudaGetLastError());
@@ -533,7 +622,8 @@ extern "C" int b200x_mel_frames_per_cta(void) { return 32; }
 
 extern "C" int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_samples, int copies, int sample_rate,
                             int n_mels, double f_min, double f_max, double amin, const double* d_sumsq,
-                            double ref_rms, int64_t rms_count, float* d_db, float* d_cta_max, void* stream) {
+                            double ref_rms, int64_t rms_count, float* d_db, int db_frames, float* d_cta_max,
+                            const int32_t* d_frame_range, int max_range_frames, void* stream) {
     B200X_REQUIRE(n_mels > 0 && n_mels <= 128 && n_mels % 32 == 0, "mel: n_mels=%d unsupported", n_mels);
     B200X_REQUIRE(n_samples > NFFT / 2 && copies > 0, "mel: bad sizes");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -546,29 +636,54 @@ extern "C" int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_sample
     p.n_frames = 1 + static_cast<int>(n_samples / HOP); p.n_mels = n_mels;
     p.fb_start = g_bank.d_start; p.fb_count = g_bank.d_count; p.fb_offset = g_bank.d_offset; p.fb_weights = g_bank.d_weights;
     p.amin = static_cast<float>(amin); p.db = d_db; p.cta_max = d_cta_max; p.frames_per_cta = b200x_mel_frames_per_cta();
-    dim3 grid(ceil_div(p.n_frames, p.frames_per_cta), copies);
+    p.db_frames = db_frames; p.frame_range = d_frame_range;
+    const int span = d_frame_range ? std::min(p.n_frames, std::max(1, max_range_frames)) : p.n_frames;
+    B200X_REQUIRE(db_frames >= span, "mel: db_frames=%d smaller than the frame span %d", db_frames, span);
+    dim3 grid(ceil_div(span, p.frames_per_cta), copies);
     mel_db_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }
 
-extern "C" int b200x_mel_normalize_resize(const float* d_db, const float* d_cta_max, int n_cta_max, int copies,
+extern "C" int b200x_mel_normalize_resize(const float* d_db, int db_frames, const float* d_cta_max, int n_cta_max, int copies,
                                           int n_frames, int n_mels, float top_db, int unbiased, float eps, int out_t,
-                                          void* d_partial, float* d_floor, void* d_img_t, void* d_img_f, int ld_f,
-                                          void* stream) {
-    B200X_REQUIRE(n_mels <= 128 && (static_cast<long long>(n_frames) * n_mels) % 4 == 0, "resize: bad sizes");
+                                          const float* d_db_base, const float* d_base_premax, const float* d_base_sufmax,
+                                          const int32_t* d_frame_range, void* d_partial, float* d_floor, void* d_img_t,
+                                          void* d_img_f, int ld_f, void* stream) {
+    B200X_REQUIRE(n_mels <= 128 && n_mels % 4 == 0, "resize: bad sizes");
+    B200X_REQUIRE(d_db_base == nullptr || (d_base_premax && d_base_sufmax && d_frame_range), "resize: baseline needs maxima and frame ranges");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int n_partial = 32;
+    StatsParams sp;
+    sp.db = d_db; sp.db_frames = db_frames; sp.n_frames = n_frames; sp.n_mels = n_mels; sp.cta_max = d_cta_max;
+    sp.n_cta_max = n_cta_max; sp.top_db = top_db; sp.base = d_db_base; sp.base_premax = d_base_premax;
+    sp.base_sufmax = d_base_sufmax; sp.frame_range = d_frame_range; sp.partial = reinterpret_cast<double2*>(d_partial);
+    sp.floor_out = d_floor;
     dim3 g1(n_partial, copies);
-    mel_stats_kernel<<<g1, 256, 0, s>>>(d_db, static_cast<long long>(n_frames) * n_mels, d_cta_max, n_cta_max, top_db,
-                                        reinterpret_cast<double2*>(d_partial), d_floor);
+    mel_stats_kernel<<<g1, 256, 0, s>>>(sp);
     B200X_CUDA_TRY(cudaGetLastError());
     ResizeParams p;
-    p.db = d_db; p.partial = reinterpret_cast<const double2*>(d_partial); p.floor_val = d_floor; p.n_partial = n_partial;
+    p.db = d_db; p.db_frames = db_frames; p.base = d_db_base; p.frame_range = d_frame_range;
+    p.partial = reinterpret_cast<const double2*>(d_partial); p.floor_val = d_floor; p.n_partial = n_partial;
     p.n_frames = n_frames; p.n_mels = n_mels; p.out_t = out_t; p.unbiased = unbiased; p.eps = eps;
     p.img_t = reinterpret_cast<__nv_bfloat16*>(d_img_t); p.img_f = reinterpret_cast<__nv_bfloat16*>(d_img_f); p.ld_f = ld_f;
     dim3 g2(ceil_div(out_t, 64), copies);
     mel_resize_kernel<<<g2, 256, 0, s>>>(p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_frame_ranges(const int32_t* d_windows, int n, int n_frames, int32_t* d_ranges, void* stream) {
+    if (n <= 0) return B200X_OK;
+    frame_ranges_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(d_windows, n, n_frames, d_ranges);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_mel_base_maxima(const float* d_db_base, int n_frames, int n_mels, float* d_premax, float* d_sufmax,
+                                     void* stream) {
+    B200X_REQUIRE(n_frames > 0 && n_frames <= 12000, "base_maxima: n_frames=%d out of range", n_frames);
+    base_maxima_kernel<<<1, 256, n_frames * sizeof(float), static_cast<cudaStream_t>(stream)>>>(d_db_base, n_frames, n_mels, d_premax, d_sufmax);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }

@@ -77,6 +77,9 @@ struct b200x_engine {
     static constexpr int s_stride = 1028;
     DevBuf wave, S;
     double ref_rms = 0.0;      // sqrt(mean(wave^2) + 1e-8)
+    // baseline of the current track for the sparse occlusion path: dB mel of istft(S) and its prefix / suffix maxima
+    DevBuf db_base, base_pre, base_suf, ranges;
+    bool baseline_valid = false;
 
     // workspace
     int64_t y_stride = 0;
@@ -145,18 +148,22 @@ int ensure_grow(DevBuf& b, size_t bytes) {
 
 // The SpecTTTra forward over `copies` waves already sitting in e->y (rows of y_stride floats, n_samples valid).
 int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* d_sumsq, int64_t rms_count, float* d_prob,
-                  float* d_logit) {
+                  float* d_logit, const int32_t* d_ranges = nullptr, int max_range = 0) {
     const b200x_model_config& c = e->cfg;
     cudaStream_t s = e->stream;
     const int n_frames = 1 + static_cast<int>(n_samples / c.hop_length);
-    const int n_cta = ceil_div(n_frames, b200x_mel_frames_per_cta());
+    const int span = d_ranges ? std::min(n_frames, std::max(1, max_range)) : n_frames;
+    const int n_cta = ceil_div(span, b200x_mel_frames_per_cta());
     const int D = e->D, T = e->T, M = copies * T;
     e->last_copies = copies;
     TIMED(KC_MEL, b200x_mel_db(e->y.as<float>(), e->y_stride, n_samples, copies, c.sample_rate, c.n_mels, c.f_min, c.f_max, c.amin,
-                           d_sumsq, e->ref_rms, rms_count, e->db.as<float>(), e->cta_max.as<float>(), s));
-    TIMED(KC_RESIZE, b200x_mel_normalize_resize(e->db.as<float>(), e->cta_max.as<float>(), n_cta, copies, n_frames, c.n_mels,
-                                         static_cast<float>(c.top_db), c.std_unbiased, c.norm_eps, c.input_temp_dim,
-                                         e->partial.p, e->floor_v.as<float>(), e->img_t.p, e->img_f.p, c.input_temp_dim, s));
+                           d_sumsq, e->ref_rms, rms_count, e->db.as<float>(), e->max_frames, e->cta_max.as<float>(), d_ranges,
+                           max_range, s));
+    TIMED(KC_RESIZE, b200x_mel_normalize_resize(e->db.as<float>(), e->max_frames, e->cta_max.as<float>(), n_cta, copies, n_frames,
+                                         c.n_mels, static_cast<float>(c.top_db), c.std_unbiased, c.norm_eps, c.input_temp_dim,
+                                         d_ranges ? e->db_base.as<float>() : nullptr, e->base_pre.as<float>(),
+                                         e->base_suf.as<float>(), d_ranges, e->partial.p, e->floor_v.as<float>(), e->img_t.p,
+                                         e->img_f.p, c.input_temp_dim, s));
     e->launches += 3;
     // tokenizers: temporal rows = t_clip consecutive time steps x n_mels; spectral rows = one mel row over time
     const int Kt = c.t_clip * c.input_spec_dim;
@@ -274,6 +281,9 @@ extern "C" int b200x_engine_create(const b200x_model_config* cfg, int copies_per
     A(e->sumsq, static_cast<size_t>(C) * sizeof(double));
     A(e->wave, static_cast<size_t>(e->y_stride) * sizeof(float));
     A(e->S, static_cast<size_t>(e->max_frames) * b200x_engine::s_stride * 2 * sizeof(float));
+    A(e->db_base, static_cast<size_t>(e->max_frames) * cfg->n_mels * sizeof(float));
+    A(e->base_pre, static_cast<size_t>(e->max_frames + 1) * sizeof(float));
+    A(e->base_suf, static_cast<size_t>(e->max_frames + 1) * sizeof(float));
     if (st != B200X_OK) { b200x_engine_destroy(e); return st; }
     cudaMemset(e->y.p, 0, e->y.bytes);
     *out = e;
@@ -285,7 +295,7 @@ extern "C" void b200x_engine_destroy(b200x_engine* e) {
     DevBuf* bufs[] = {&e->tok_t_w, &e->tok_s_w, &e->tok_t_b, &e->tok_s_b, &e->pe_t, &e->pe_s, &e->np_t_g, &e->np_t_b, &e->np_s_g,
                       &e->np_s_b, &e->fn_g, &e->fn_b, &e->cls_w, &e->wave, &e->S, &e->y, &e->db, &e->cta_max, &e->partial,
                       &e->floor_v, &e->img_t, &e->img_f, &e->x, &e->h, &e->qkv, &e->att, &e->hid, &e->head_part, &e->prob,
-                      &e->logit, &e->sumsq, &e->windows, &e->gains, &e->masks, &e->stems, &e->delta, &e->order, &e->map};
+                      &e->logit, &e->sumsq, &e->db_base, &e->base_pre, &e->base_suf, &e->ranges, &e->windows, &e->gains, &e->masks, &e->stems, &e->delta, &e->order, &e->map};
     for (DevBuf* b : bufs) b->release();
     for (LayerW& w : e->layers) {
         DevBuf* lb[] = {&w.qkv_w, &w.qkv_b, &w.proj_w, &w.proj_b, &w.fc1_w, &w.fc1_b, &w.fc2_w, &w.fc2_b, &w.n1_g, &w.n1_b, &w.n2_g, &w.n2_b};
@@ -420,6 +430,7 @@ extern "C" int b200x_engine_set_track(b200x_engine* e, const float* wave, int64_
     e->n_time = 1 + static_cast<int>(n_samples / e->cfg.hop_length);
     B200X_TRY(b200x_stft(e->wave.as<float>(), n_samples, e->cfg.n_fft, e->cfg.hop_length, 0, e->S.p, b200x_engine::s_stride, e->stream));
     e->launches += 1;
+    e->baseline_valid = false;
     e->ref_rms = -1.0;   // computed lazily (ensure_ref_rms) when a loudness-normalised FBP sweep asks for it
     // the tail of every y row beyond hop*(n_time-1) must read as zero padding (spectrogram_explainability.py:679-680)
     B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, e->y.bytes, e->stream));
@@ -449,10 +460,40 @@ extern "C" int b200x_engine_get_spectrogram(b200x_engine* e, float* spec_host) {
 }
 
 namespace {
+// Baseline for the sparse occlusion path: y_base = istft(S) padded to len(y), its dB mel spectrogram and maxima.
+int ensure_baseline(b200x_engine* e) {
+    if (e->baseline_valid) return B200X_OK;
+    const b200x_model_config& c = e->cfg;
+    const int64_t out_len = static_cast<int64_t>(c.hop_length) * (e->n_time - 1);
+    const int n_frames = 1 + static_cast<int>(e->L / c.hop_length);
+    TIMED(KC_ISTFT, b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, 1, B200X_MASK_NONE, nullptr, 0.f, nullptr,
+                                 e->y.as<float>(), e->y_stride, nullptr, nullptr, 0, e->stream));
+    if (e->L > out_len)
+        B200X_CUDA_TRY(cudaMemsetAsync(e->y.as<float>() + out_len, 0, (e->L - out_len) * sizeof(float), e->stream));
+    TIMED(KC_MEL, b200x_mel_db(e->y.as<float>(), e->y_stride, e->L, 1, c.sample_rate, c.n_mels, c.f_min, c.f_max, c.amin, nullptr, 0.0,
+                         0, e->db_base.as<float>(), e->max_frames, e->cta_max.as<float>(), nullptr, 0, e->stream));
+    TIMED(KC_OTHER, b200x_mel_base_maxima(e->db_base.as<float>(), n_frames, c.n_mels, e->base_pre.as<float>(), e->base_suf.as<float>(), e->stream));
+    e->launches += 3;
+    e->baseline_valid = true;
+    return B200X_OK;
+}
+
 // shared body of the occlusion / FBP sweeps: perturb in the iSTFT load stage, classify, collect probabilities
 int sweep(b200x_engine* e, int mode, int n, const int32_t* d_windows, float occ_value, const float* d_gains, bool rms,
-          float* d_prob_out) {
+          float* d_prob_out, int max_range = 0) {
     const int64_t out_len = static_cast<int64_t>(e->cfg.hop_length) * (e->n_time - 1);
+    // occlusion: only classifier frames [t0-4, t1+4) differ from the unperturbed track (iSTFT linearity); everything
+    // else is read from the per-track baseline.  Band gains change every frame, so FBP takes the dense path.
+    const bool sparse = (mode == B200X_MASK_OCCLUDE) && max_range > 0 && max_range < e->n_time;
+    const int32_t* d_ranges = nullptr;
+    if (sparse) {
+        B200X_TRY(ensure_baseline(e));
+        B200X_TRY(ensure_grow(e->ranges, static_cast<size_t>(n) * 2 * sizeof(int32_t)));
+        const int n_frames_cls = 1 + static_cast<int>(e->L / e->cfg.hop_length);
+        TIMED(KC_OTHER, b200x_frame_ranges(d_windows, n, n_frames_cls, e->ranges.as<int32_t>(), e->stream));
+        e->launches += 1;
+        d_ranges = e->ranges.as<int32_t>();
+    }
     for (int c0 = 0; c0 < n; c0 += e->C) {
         const int m = std::min(e->C, n - c0);
         double* sumsq = nullptr;
@@ -462,14 +503,15 @@ int sweep(b200x_engine* e, int mode, int n, const int32_t* d_windows, float occ_
         }
         TIMED(KC_ISTFT, b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, d_windows ? d_windows + 4 * c0 : nullptr,
                                      occ_value, d_gains ? d_gains + static_cast<size_t>(c0) * b200x_engine::n_freq : nullptr,
-                                     e->y.as<float>(), e->y_stride, sumsq, e->stream));
+                                     e->y.as<float>(), e->y_stride, sumsq, d_ranges ? d_ranges + 2 * c0 : nullptr, max_range, e->stream));
         e->launches += 1;
         // occlusion: the reference pads/trims y_occ to len(y); FBP feeds the iSTFT output as is (dsp_band_ops.py:580-586)
         const int64_t n_cls = (mode == B200X_MASK_BAND_GAIN) ? out_len : e->L;
         if (n_cls > out_len)   // zero padding of the tail (spectrogram_explainability.py:679-680)
             B200X_CUDA_TRY(cudaMemset2DAsync(e->y.as<float>() + out_len, e->y_stride * sizeof(float), 0,
                                              (n_cls - out_len) * sizeof(float), m, e->stream));
-        B200X_TRY(forward_chunk(e, m, n_cls, sumsq, out_len, d_prob_out + c0, e->logit.as<float>() + c0));
+        B200X_TRY(forward_chunk(e, m, n_cls, sumsq, out_len, d_prob_out + c0, e->logit.as<float>() + c0,
+                                d_ranges ? d_ranges + 2 * c0 : nullptr, max_range));
     }
     return B200X_OK;
 }
@@ -482,18 +524,28 @@ extern "C" int b200x_engine_occlusion_sweep(b200x_engine* e, const int32_t* wind
     B200X_REQUIRE(windows && prob && n > 0, "occlusion_sweep: bad argument");
     B200X_TRY(ensure_prob(e, n));
     const int32_t* d_win = windows;
+    std::vector<int32_t> host_copy;
+    const int32_t* h_win = windows;
+    if (on_device) {                       // the (tiny) window list is validated on the host in both cases
+        host_copy.resize(static_cast<size_t>(n) * 4);
+        B200X_CUDA_TRY(cudaMemcpyAsync(host_copy.data(), windows, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, e->stream));
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        h_win = host_copy.data();
+    }
+    int max_range = 0;
+    for (int i = 0; i < n; ++i) {
+        const int32_t* w = h_win + 4 * i;
+        B200X_REQUIRE(w[0] >= 0 && w[0] <= w[1] && w[1] <= e->n_time && w[2] >= 0 && w[2] <= w[3] && w[3] <= b200x_engine::n_freq,
+                      "occlusion_sweep: window %d = (%d,%d,%d,%d) outside the %dx%d spectrogram", i, w[0], w[1], w[2], w[3],
+                      b200x_engine::n_freq, e->n_time);
+        max_range = std::max(max_range, w[1] - w[0] + 8);
+    }
     if (!on_device) {
-        for (int i = 0; i < n; ++i) {
-            const int32_t* w = windows + 4 * i;
-            B200X_REQUIRE(w[0] >= 0 && w[0] <= w[1] && w[1] <= e->n_time && w[2] >= 0 && w[2] <= w[3] && w[3] <= b200x_engine::n_freq,
-                          "occlusion_sweep: window %d = (%d,%d,%d,%d) outside the %dx%d spectrogram", i, w[0], w[1], w[2], w[3],
-                          b200x_engine::n_freq, e->n_time);
-        }
         B200X_TRY(ensure_grow(e->windows, static_cast<size_t>(n) * 4 * sizeof(int32_t)));
         B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, windows, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, e->stream));
         d_win = e->windows.as<int32_t>();
     }
-    B200X_TRY(sweep(e, B200X_MASK_OCCLUDE, n, d_win, occlusion_value, nullptr, false, e->prob.as<float>()));
+    B200X_TRY(sweep(e, B200X_MASK_OCCLUDE, n, d_win, occlusion_value, nullptr, false, e->prob.as<float>(), max_range));
     B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
     return B200X_OK;
@@ -567,7 +619,7 @@ int audio_out(b200x_engine* e, int mode, const int32_t* windows, const float* ga
         const int m = std::min(e->C, n - c0);
         TIMED(KC_ISTFT, b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, windows ? e->windows.as<int32_t>() + 4 * c0 : nullptr,
                                      occ_value, gains ? e->gains.as<float>() + static_cast<size_t>(c0) * b200x_engine::n_freq : nullptr,
-                                     e->y.as<float>(), e->y_stride, nullptr, e->stream));
+                                     e->y.as<float>(), e->y_stride, nullptr, nullptr, 0, e->stream));
         e->launches += 1;
         if (seg_stride > 0) {
             for (int i = 0; i < m; ++i) {

@@ -57,33 +57,50 @@ int b200x_stft(const float* d_wave, int64_t n_samples, int n_fft, int hop, int r
 /* Batched librosa.istft of `copies` perturbed versions of one spectrogram; the perturbation is applied in the
  * load stage (mode = B200X_MASK_*), d_windows int32 [copies][4] = t0,t1,f0,f1, d_gains float [copies][1025].
  * Writes hop*(n_frames-1) samples per copy at d_y + copy*y_stride; d_sumsq (optional, pre-zeroed double[copies])
- * receives sum(y^2) for match_rms.  replaces: src/spectrogram_explainability.py:670-680, dsp_band_ops.py:578-580 */
+ * receives sum(y^2) for match_rms.  d_frame_range (optional, int32 [copies][2] = [ma, mb) from b200x_frame_ranges,
+ * max_range_frames = max(mb - ma)): only the samples that classifier frames [ma, mb) read are synthesised - by
+ * linearity of the iSTFT every other sample equals the unperturbed track's.
+ * replaces: src/spectrogram_explainability.py:670-680, dsp_band_ops.py:578-580 */
 int b200x_istft_masked(const void* d_spec, int spec_stride, int n_frames, int copies, int mode,
                        const int32_t* d_windows, float occlusion_value, const float* d_gains, float* d_y,
-                       int64_t y_stride, double* d_sumsq, void* stream);
+                       int64_t y_stride, double* d_sumsq, const int32_t* d_frame_range, int max_range_frames,
+                       void* stream);
+
+/* classifier frames [ma, mb) = [t0 - 4, t1 + 4) whose input samples an occlusion window t0,t1,f0,f1 can change */
+int b200x_frame_ranges(const int32_t* d_windows, int n, int n_frames, int32_t* d_ranges, void* stream);
 
 /* Classifier front-end (sonics FeatureExtractor = torchaudio MelSpectrogram + AmplitudeToDB, third-party):
- * reflect-padded STFT -> power -> HTK mel -> 10 log10(max(., amin)).  d_db float [copies][n_frames][n_mels];
- * d_cta_max float [copies][ceil(n_frames / b200x_mel_frames_per_cta())].  If d_sumsq != NULL the samples are
- * scaled by ref_rms / sqrt(sumsq/rms_count + 1e-8) first (match_rms, src/dsp_band_ops.py:228-233). */
+ * reflect-padded STFT -> power -> HTK mel -> 10 log10(max(., amin)).  d_db float [copies][db_frames][n_mels] (row
+ * t - ma when d_frame_range is given, else row t); d_cta_max float [copies][ceil(span / b200x_mel_frames_per_cta())].
+ * If d_sumsq != NULL the samples are scaled by ref_rms / sqrt(sumsq/rms_count + 1e-8) first (match_rms,
+ * src/dsp_band_ops.py:228-233). */
 int b200x_mel_frames_per_cta(void);
 int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_samples, int copies, int sample_rate, int n_mels,
                  double f_min, double f_max, double amin, const double* d_sumsq, double ref_rms, int64_t rms_count,
-                 float* d_db, float* d_cta_max, void* stream);
+                 float* d_db, int db_frames, float* d_cta_max, const int32_t* d_frame_range, int max_range_frames,
+                 void* stream);
+
+/* prefix / suffix maxima of a baseline dB spectrogram: premax[m] = max over frames < m, sufmax[m] = max over frames >= m
+ * (m = 0..n_frames), used for the per-copy top_db floor when only frames [ma, mb) were recomputed */
+int b200x_mel_base_maxima(const float* d_db_base, int n_frames, int n_mels, float* d_premax, float* d_sufmax, void* stream);
 
 /* top_db clamp, (x-mean)/(std+eps), F.interpolate(bilinear) along time to out_t, bf16, in both tokenizer operand
- * layouts: d_img_t [copies][out_t][n_mels], d_img_f [copies][n_mels][ld_f].  d_partial: 32*copies double2 scratch. */
-int b200x_mel_normalize_resize(const float* d_db, const float* d_cta_max, int n_cta_max, int copies, int n_frames,
-                               int n_mels, float top_db, int unbiased, float eps, int out_t, void* d_partial,
-                               float* d_floor, void* d_img_t, void* d_img_f, int ld_f, void* stream);
+ * layouts: d_img_t [copies][out_t][n_mels], d_img_f [copies][n_mels][ld_f].  d_partial: 32*copies double2 scratch.
+ * With d_db_base (+ maxima + d_frame_range) frames outside [ma, mb) are read from the baseline spectrogram. */
+int b200x_mel_normalize_resize(const float* d_db, int db_frames, const float* d_cta_max, int n_cta_max, int copies,
+                               int n_frames, int n_mels, float top_db, int unbiased, float eps, int out_t,
+                               const float* d_db_base, const float* d_base_premax, const float* d_base_sufmax,
+                               const int32_t* d_frame_range, void* d_partial, float* d_floor, void* d_img_t,
+                               void* d_img_f, int ld_f, void* stream);
 
 /* y[b] = sum_i masks[b][i] * stems[i]   (src/lime_explainer.py:283-301 composition) */
 int b200x_mix_stems(const float* d_stems, int64_t n_samples, int n_stems, const uint8_t* d_masks, int copies,
                     float* d_y, int64_t y_stride, void* stream);
 
 /* tcgen05 GEMM  C[M,N] = A[M,K] . W[N,K]^T, bf16 operands (row-major, K contiguous), fp32 accumulation in TMEM,
- * fused epilogue per B200X_GEMM_OUT_*.  block_n in {128,192,208,256}.  Replaces every nn.Linear / Conv1d
- * contraction of the third-party SpecTTTra forward. */
+ * fused epilogue per B200X_GEMM_OUT_*.  block_n in {128,192,208,256}.  B200X_GEMM_OUT_F32_RESID accumulates in place
+ * (d_resid must equal d_out; TMA reduce-add).  Replaces every nn.Linear / Conv1d contraction of the third-party
+ * SpecTTTra forward. */
 int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n, void* d_out,
                     int ldc, int out_mode, const float* d_bias, int act_gelu, const float* d_resid, const float* d_pe,
                     int group_in, int group_out, int group_off, void* stream);

@@ -93,10 +93,11 @@ def attention(x, sd, p, cfg, gemm_dtype):
     s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
     pattn = torch.softmax(s, dim=-1)
     if gemm_dtype == "bf16":
-        # engine: P = exp(s - m) rounded to bf16 for the PV contraction, normalised by the fp32 row sum
+        # engine: P = exp(s - m) in bf16 for the PV contraction, normalised by the row sum (of the same bf16 values)
         m = s.max(dim=-1, keepdim=True).values
         e = torch.exp(s - m)
-        o = (_q(e, gemm_dtype) @ v) / e.sum(dim=-1, keepdim=True)
+        eq = _q(e, gemm_dtype)
+        o = (eq @ v) / eq.sum(dim=-1, keepdim=True)
     else:
         o = pattn @ v
     o = o.transpose(1, 2).reshape(B, N, D)

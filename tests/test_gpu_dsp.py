@@ -40,7 +40,7 @@ def _gpu_istft(S, n_frames, copies, mode, windows=None, occ=0.0, gains=None, sum
     ss = torch.zeros(copies, dtype=torch.float64, device="cuda") if sumsq else None
     w = torch.from_numpy(np.ascontiguousarray(windows, dtype=np.int32)).cuda() if windows is not None else None
     g = torch.from_numpy(np.ascontiguousarray(gains, dtype=np.float32)).cuda() if gains is not None else None
-    ok(lib().b200x_istft_masked(P(S), STRIDE, n_frames, copies, mode, P(w), occ, P(g), P(y), L + 8, P(ss), P(None)))
+    ok(lib().b200x_istft_masked(P(S), STRIDE, n_frames, copies, mode, P(w), occ, P(g), P(y), L + 8, P(ss), P(None), 0, P(None)))
     return y[:, :L].cpu(), (ss.cpu() if sumsq else None)
 
 
@@ -101,7 +101,7 @@ def _gpu_mel_db(y2d, n_samples, sumsq=None, ref_rms=0.0):
     db = torch.full((copies, n_frames, 128), float("nan"), device="cuda")
     cmax = torch.zeros(copies, n_cta, device="cuda")
     ok(lib().b200x_mel_db(P(y2d), y2d.shape[1], n_samples, copies, cfg.sample_rate, cfg.n_mels, cfg.f_min, cfg.f_max, cfg.amin,
-                          P(sumsq), ref_rms, n_samples, P(db), P(cmax), P(None)))
+                          P(sumsq), ref_rms, n_samples, P(db), n_frames, P(cmax), P(None), 0, P(None)))
     return db, cmax, n_frames, n_cta
 
 
@@ -132,8 +132,9 @@ def test_mel_normalize_resize_matches_oracle():
     img_f = torch.zeros(2, 128, cfg.input_temp_dim, dtype=torch.bfloat16, device="cuda")
     partial = torch.zeros(2 * 32 * 2, dtype=torch.float64, device="cuda")
     floor = torch.zeros(2, device="cuda")
-    ok(lib().b200x_mel_normalize_resize(P(db), P(cmax), n_cta, 2, n_frames, 128, cfg.top_db, 1, cfg.norm_eps, cfg.input_temp_dim,
-                                        P(partial), P(floor), P(img_t), P(img_f), cfg.input_temp_dim, P(None)))
+    ok(lib().b200x_mel_normalize_resize(P(db), n_frames, P(cmax), n_cta, 2, n_frames, 128, cfg.top_db, 1, cfg.norm_eps,
+                                        cfg.input_temp_dim, P(None), P(None), P(None), P(None), P(partial), P(floor), P(img_t),
+                                        P(img_f), cfg.input_temp_dim, P(None)))
     ref = spectttra.resize(dsp.mel_frontend(torch.from_numpy(ys), cfg, "norm"), cfg)     # [B, 128, 3744]
     got_f = img_f.float().cpu()
     got_t = img_t.float().cpu().transpose(1, 2)
@@ -166,3 +167,56 @@ def test_mix_stems():
     ok(lib().b200x_mix_stems(P(D(st)), st.shape[1], 4, P(D(masks)), 4, P(out), st.shape[1], P(None)))
     ref = masks.astype(np.float32) @ st
     assert np.abs(out.cpu().numpy() - ref).max() < 1e-6
+
+
+def test_sparse_occlusion_path_is_bit_identical_to_dense():
+    """iSTFT restricted to the samples that classifier frames [t0-4, t1+4) read + baseline spectrogram for every other
+    frame == the dense computation, bit for bit (same arithmetic on the same inputs)."""
+    cfg = ALPHA_120S
+    y = _track(20.0, "UDIO")
+    L = len(y)
+    S = _gpu_stft(y)
+    n_frames = S.shape[0]
+    wins = np.array([[0, 40, 0, 200], [3, 50, 10, 61], [4, 70, 0, 1025], [200, 328, 500, 551], [n_frames - 60, n_frames, 900, 1025],
+                     [n_frames - 64, n_frames - 4, 0, 51], [100, 100, 0, 10]], np.int32)
+    n = len(wins)
+    d_w = D(wins)
+    # dense reference
+    yd = torch.zeros(n, L + 8, device="cuda")
+    ok(lib().b200x_istft_masked(P(S), STRIDE, n_frames, n, 1, P(d_w), 0.0, P(None), P(yd), L + 8, P(None), P(None), 0, P(None)))
+    db_d, cmax_d, _, n_cta_d = _gpu_mel_db(yd, L)
+    img_t_d = torch.zeros(n, cfg.input_temp_dim, 128, dtype=torch.bfloat16, device="cuda")
+    img_f_d = torch.zeros(n, 128, cfg.input_temp_dim, dtype=torch.bfloat16, device="cuda")
+    part = torch.zeros(n * 64, dtype=torch.float64, device="cuda")
+    fl_d = torch.zeros(n, device="cuda")
+    ok(lib().b200x_mel_normalize_resize(P(db_d), n_frames, P(cmax_d), n_cta_d, n, n_frames, 128, cfg.top_db, 1, cfg.norm_eps,
+                                        cfg.input_temp_dim, P(None), P(None), P(None), P(None), P(part), P(fl_d), P(img_t_d),
+                                        P(img_f_d), cfg.input_temp_dim, P(None)))
+    # baseline + sparse
+    yb = torch.zeros(1, L + 8, device="cuda")
+    ok(lib().b200x_istft_masked(P(S), STRIDE, n_frames, 1, 0, P(None), 0.0, P(None), P(yb), L + 8, P(None), P(None), 0, P(None)))
+    db_b, _, _, _ = _gpu_mel_db(yb, L)
+    pre = torch.zeros(n_frames + 1, device="cuda")
+    suf = torch.zeros(n_frames + 1, device="cuda")
+    ok(lib().b200x_mel_base_maxima(P(db_b), n_frames, 128, P(pre), P(suf), P(None)))
+    assert float(suf[0]) == float(db_b.max()) and float(pre[n_frames]) == float(db_b.max())
+    rng = torch.zeros(n, 2, dtype=torch.int32, device="cuda")
+    ok(lib().b200x_frame_ranges(P(d_w), n, n_frames, P(rng), P(None)))
+    max_range = int((wins[:, 1] - wins[:, 0]).max()) + 8
+    ys = torch.full((n, L + 8), float("nan"), device="cuda")      # untouched samples must never be read
+    ok(lib().b200x_istft_masked(P(S), STRIDE, n_frames, n, 1, P(d_w), 0.0, P(None), P(ys), L + 8, P(None), P(rng), max_range, P(None)))
+    n_cta_s = -(-min(n_frames, max_range) // lib().b200x_mel_frames_per_cta())
+    db_s = torch.full((n, n_frames, 128), float("nan"), device="cuda")
+    cmax_s = torch.zeros(n, n_cta_s, device="cuda")
+    ok(lib().b200x_mel_db(P(ys), L + 8, L, n, cfg.sample_rate, 128, cfg.f_min, cfg.f_max, cfg.amin, P(None), 0.0, L, P(db_s), n_frames,
+                          P(cmax_s), P(rng), max_range, P(None)))
+    img_t_s = torch.zeros_like(img_t_d)
+    img_f_s = torch.zeros_like(img_f_d)
+    fl_s = torch.zeros(n, device="cuda")
+    ok(lib().b200x_mel_normalize_resize(P(db_s), n_frames, P(cmax_s), n_cta_s, n, n_frames, 128, cfg.top_db, 1, cfg.norm_eps,
+                                        cfg.input_temp_dim, P(db_b), P(pre), P(suf), P(rng), P(part), P(fl_s), P(img_t_s),
+                                        P(img_f_s), cfg.input_temp_dim, P(None)))
+    assert torch.equal(fl_s, fl_d)
+    assert torch.equal(img_t_s, img_t_d) and torch.equal(img_f_s, img_f_d)
+    r = rng.cpu().numpy()
+    assert r[-1].tolist() == [0, 0] and r[0].tolist() == [0, 44] and r[4].tolist() == [n_frames - 64, n_frames]

@@ -83,17 +83,24 @@ _lib.check(lib.b200x_stft(P(wave), L, 2048, 512, 0, P(S), 1028, P(None)))
 y = torch.zeros(copies, L + 8, device=dev)
 wins = torch.tensor([[1024, 2048, 100, 151]] * copies, dtype=torch.int32, device=dev)
 timeit(lambda: _lib.check(lib.b200x_stft(P(wave), L, 2048, 512, 0, P(S), 1028, P(None))), name="stft (1 track)", bytes_=L * 4 + n_frames * 1025 * 8)
-t_i = timeit(lambda: _lib.check(lib.b200x_istft_masked(P(S), 1028, n_frames, copies, 1, P(wins), 0.0, P(None), P(y), L + 8, P(None), P(None))),
+t_i = timeit(lambda: _lib.check(lib.b200x_istft_masked(P(S), 1028, n_frames, copies, 1, P(wins), 0.0, P(None), P(y), L + 8, P(None), P(None), 0, P(None))),
              name=f"istft_masked x{copies}", bytes_=copies * (n_frames * 1025 * 8 + L * 4), iters=5)
 n_cta = -(-n_frames // lib.b200x_mel_frames_per_cta())
 db = torch.zeros(copies, n_frames, 128, device=dev)
 cmax = torch.zeros(copies, n_cta, device=dev)
-t_m = timeit(lambda: _lib.check(lib.b200x_mel_db(P(y), L + 8, L, copies, 16000, 128, 20.0, 8000.0, 1e-10, P(None), 0.0, L, P(db), P(cmax), P(None))),
+t_m = timeit(lambda: _lib.check(lib.b200x_mel_db(P(y), L + 8, L, copies, 16000, 128, 20.0, 8000.0, 1e-10, P(None), 0.0, L, P(db), n_frames, P(cmax), P(None), 0, P(None))),
              name=f"mel_db x{copies}", bytes_=copies * (L * 4 + n_frames * 128 * 4), iters=5)
 img_t = torch.zeros(copies, 3744, 128, dtype=torch.bfloat16, device=dev)
 img_f = torch.zeros(copies, 128, 3744, dtype=torch.bfloat16, device=dev)
 part = torch.zeros(copies * 64, dtype=torch.float64, device=dev)
 fl = torch.zeros(copies, device=dev)
-t_r = timeit(lambda: _lib.check(lib.b200x_mel_normalize_resize(P(db), P(cmax), n_cta, copies, n_frames, 128, 80.0, 1, 1e-6, 3744, P(part), P(fl), P(img_t), P(img_f), 3744, P(None))),
+t_r = timeit(lambda: _lib.check(lib.b200x_mel_normalize_resize(P(db), n_frames, P(cmax), n_cta, copies, n_frames, 128, 80.0, 1, 1e-6, 3744, P(None), P(None), P(None), P(None), P(part), P(fl), P(img_t), P(img_f), 3744, P(None))),
              name=f"normalize+resize x{copies}", iters=5)
+rng = torch.zeros(copies, 2, dtype=torch.int32, device=dev)
+_lib.check(lib.b200x_frame_ranges(P(wins), copies, n_frames, P(rng), P(None)))
+t_is = timeit(lambda: _lib.check(lib.b200x_istft_masked(P(S), 1028, n_frames, copies, 1, P(wins), 0.0, P(None), P(y), L + 8, P(None), P(rng), 1032, P(None))),
+              name=f"istft_masked sparse x{copies}", iters=5)
+t_ms = timeit(lambda: _lib.check(lib.b200x_mel_db(P(y), L + 8, L, copies, 16000, 128, 20.0, 8000.0, 1e-10, P(None), 0.0, L, P(db), n_frames, P(cmax), P(rng), 1032, P(None))),
+              name=f"mel_db sparse x{copies}", iters=5)
+print(f"DSP sparse per eval: {(t_is + t_ms + t_r) / copies:7.1f} us")
 print(f"DSP per eval: {(t_i + t_m + t_r) / copies:7.1f} us   transformer per eval: {12 * total / copies:7.1f} us")
