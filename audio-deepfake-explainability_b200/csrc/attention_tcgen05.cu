@@ -5,8 +5,9 @@
 // tensor pipe: while the softmax warps of tile A work on S_A, the MMAs of tile B run, and vice versa.
 //   warp 0     : TMA producer - Q_A, Q_B once; K / V tiles through a 4-stage mbarrier ring
 //                (3-D tensor map over [copy][token][3 * heads * 64], 128-byte swizzle, OOB rows zero-filled)
-//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer:
-//                S_x = Q_x K^T (SS form, fp32 in TMEM),  O_x += P_x V (P_x read from TMEM, V MN-major in shared memory)
+//   warp 1, 10 : one tcgen05.mma issuer thread per query tile (warp 1 also owns the TMEM allocation):
+//                S_x = Q_x K^T (SS form, fp32 in TMEM),  O_x += P_x V (P_x read from TMEM, V MN-major in shared memory);
+//                two issuers keep the tiles' dependency chains (softmax -> PV -> next S) independent of each other
 //   warps 2-5  : softmax of tile A, warps 6-9: softmax of tile B.  One query row per thread (TMEM lane == row, so row
 //                max / sum need no shuffles); exp2 with 1/sqrt(d) folded in; the running reference max is only replaced
 //                (and O rescaled) when a tile's row max exceeds it by more than 2^8, otherwise scores stream through
@@ -18,7 +19,7 @@
 
 namespace b200x {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 352;       // warp 0 TMA, 1 MMA(A), 2-5 softmax(A), 6-9 softmax(B), 10 MMA(B)
 constexpr int ATT_TILE = 128;
 constexpr int ATT_HD = 64;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_HD * 2;     // 16 KB
@@ -33,6 +34,7 @@ struct AttnParams {
     int heads;
     __nv_bfloat16* out;   // [copies * tokens, heads * 64]
     float scale_log2;     // (1/sqrt(64)) * log2(e)
+    int dbg;              // diagnostic variants (0 = normal): 1 no MUFU, 2 no S loads, 3 no P stores, 4 no softmax work
 };
 
 // 32 (or, for a tail chunk, 16) scores -> p = 2^(s*c - m_ref*c) -> packed bf16 in TMEM; accumulates the row sum / tile max.
@@ -40,7 +42,7 @@ struct AttnParams {
 // unit shares the MUFU pipe, which is what bounds this kernel.  The row sum is taken over the TRUNCATED values, so the
 // softmax weights stay exactly normalised and carry the same error variance as round-to-nearest, without bias.
 __device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], bool wide, uint32_t tP_col, float c, float mc,
-                                              float& acc, float& mt) {
+                                              float& acc, float& mt, int dbg = 0) {
     uint32_t pk[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -48,34 +50,44 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], bool wide
         if (wide || i < 8) {
             const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
             mt = fmax3(mt, s0, s1);
-            b0 = __float_as_uint(ex2_approx(fmaf(s0, c, -mc))) & 0xFFFF0000u;
-            b1 = __float_as_uint(ex2_approx(fmaf(s1, c, -mc))) & 0xFFFF0000u;
+            if (dbg == 1) {
+                b0 = __float_as_uint(fmaf(s0, c, -mc)) & 0xFFFF0000u;
+                b1 = __float_as_uint(fmaf(s1, c, -mc)) & 0xFFFF0000u;
+            } else {
+                b0 = __float_as_uint(ex2_approx(fmaf(s0, c, -mc))) & 0xFFFF0000u;
+                b1 = __float_as_uint(ex2_approx(fmaf(s1, c, -mc))) & 0xFFFF0000u;
+            }
         }
         acc += __uint_as_float(b0) + __uint_as_float(b1);
         pk[i] = __byte_perm(b0, b1, 0x7632);      // low half = bf16(s0), high half = bf16(s1)
     }
-    tmem_st16(tP_col, pk);                     // a 16-column tail chunk stores 8 meaningful + 8 zero words (never read)
+    if (dbg != 3) tmem_st16(tP_col, pk);       // a 16-column tail chunk stores 8 meaningful + 8 zero words (never read)
 }
 
 // One streaming pass over a score tile.  The TMEM load of chunk i+1 is in flight while chunk i is exponentiated
 // (two register buffers; a buffer is only read after the tcgen05.wait::ld that follows its load).
-__device__ __forceinline__ void softmax_pass(uint32_t tS, uint32_t tP, int nk, float c, float mc, float& acc, float& mt) {
+__device__ __forceinline__ void softmax_pass(uint32_t tS, uint32_t tP, int nk, float c, float mc, float& acc, float& mt, int dbg = 0) {
     acc = 0.f;
     mt = -INFINITY;
+    if (dbg == 4) { acc = 1.f; mt = mc / c; return; }
     uint32_t ra[32], rb[32];
-    if (nk >= 32) tmem_ld32(tS, ra); else tmem_ld16(tS, ra);
+    if (dbg == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ra[i] = rb[i] = __float_as_uint(mc / c - 0.001f * i);
+    }
+    if (dbg != 2) { if (nk >= 32) tmem_ld32(tS, ra); else tmem_ld16(tS, ra); }
 #pragma unroll
     for (int ci = 0; ci < ATT_TILE / 32; ++ci) {
         const int col = ci * 32;
         if (col < nk) {
             tmem_wait_ld();
             const int nxt = col + 32;
-            if (nxt < nk) {
+            if (nxt < nk && dbg != 2) {
                 if ((ci & 1) == 0) { if (nxt + 32 <= nk) tmem_ld32(tS + nxt, rb); else tmem_ld16(tS + nxt, rb); }
                 else               { if (nxt + 32 <= nk) tmem_ld32(tS + nxt, ra); else tmem_ld16(tS + nxt, ra); }
             }
-            if ((ci & 1) == 0) softmax_chunk(ra, col + 32 <= nk, tP + col / 2, c, mc, acc, mt);
-            else               softmax_chunk(rb, col + 32 <= nk, tP + col / 2, c, mc, acc, mt);
+            if ((ci & 1) == 0) softmax_chunk(ra, col + 32 <= nk, tP + col / 2, c, mc, acc, mt, dbg);
+            else               softmax_chunk(rb, col + 32 <= nk, tP + col / 2, c, mc, acc, mt, dbg);
         }
     }
 }
@@ -109,7 +121,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         mbar_init(q_full, 1);
         for (int s = 0; s < ATT_KV_STAGES; ++s) {
             mbar_init(&kv_full[s], 1);
-            mbar_init(&kv_empty[s], 1);
+            mbar_init(&kv_empty[s], nq);
         }
         for (int x = 0; x < 2; ++x) {
             mbar_init(&s_full[x], 1);
@@ -138,56 +150,56 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * hidden + head * ATT_HD, j * ATT_TILE, copy);
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+    } else if (warp == 1 || warp == 10) {
+        const int x = (warp == 1) ? 0 : 1;                // query tile served by this issuer
+        if (lane == 0 && x < nq) {
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_TILE, ATT_HD, true);
-            const uint32_t q_addr = smem_u32(sQ);
-            auto issue_s = [&](int x, int j) {            // S_x = Q_x K_j^T
-                const int st = j % ATT_KV_STAGES;
+            const uint32_t tS = tmem_base + ATT_S_COL + x * ATT_TILE;
+            const uint32_t tO = tmem_base + ATT_O_COL + x * ATT_HD;
+            const uint32_t tP = tmem_base + ATT_P_COL + x * ATT_HD;
+            const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ) + x * ATT_TILE_BYTES, 16, 1024);
+            const uint64_t k_desc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t v_desc0 = make_smem_desc_sw128(smem_u32(sV), 16384, 1024);
+            auto issue_s = [&](int j) {                   // S_x = Q_x K_j^T
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
                 const uint32_t idesc_s = make_idesc_bf16(ATT_TILE, nk, false);
-                const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+                const uint64_t kd = k_desc0 + static_cast<uint64_t>((j % ATT_KV_STAGES) * (ATT_TILE_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < ATT_HD / 16; ++k)
-                    umma_ss(tmem_base + ATT_S_COL + x * ATT_TILE,
-                            make_smem_desc_sw128(q_addr + x * ATT_TILE_BYTES + k * 32, 16, 1024),
-                            make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+                if (!(p.dbg & 16))
+                for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, q_desc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
                 umma_commit(&s_full[x]);
             };
-            auto issue_pv = [&](int x, int j) {           // O_x += P_x V_j
-                const int st = j % ATT_KV_STAGES;
+            auto issue_pv = [&](int j) {                  // O_x += P_x V_j
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
-                const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
-                for (int ks = 0; ks < nk / 16; ++ks)
-                    umma_ts(tmem_base + ATT_O_COL + x * ATT_HD, tmem_base + ATT_P_COL + x * ATT_HD + ks * 8,
-                            make_smem_desc_sw128(v_addr + ks * 2048, 16384, 1024), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                const uint64_t vd = v_desc0 + static_cast<uint64_t>((j % ATT_KV_STAGES) * (ATT_TILE_BYTES >> 4));
+                if (p.dbg & 8) return;
+                if (nk == ATT_TILE) {
+#pragma unroll
+                    for (int ks = 0; ks < ATT_TILE / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                } else {
+                    for (int ks = 0; ks < nk / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                }
             };
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
             tc_fence_after();
-            for (int x = 0; x < nq; ++x) issue_s(x, 0);
+            issue_s(0);
             for (int j = 0; j < nkv; ++j) {
-                const int st = j % ATT_KV_STAGES;
-                const bool more = j + 1 < nkv;
-                for (int x = 0; x < nq; ++x) {
-                    mbar_wait(&p_ready[x], j & 1);
+                mbar_wait(&p_ready[x], j & 1);
+                tc_fence_after();
+                issue_pv(j);
+                umma_commit(&kv_empty[j % ATT_KV_STAGES]);              // this tile is done with K_j / V_j
+                if (j + 1 < nkv) {
+                    mbar_wait(&kv_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
                     tc_fence_after();
-                    issue_pv(x, j);
-                    if (x == nq - 1) umma_commit(&kv_empty[st]);       // both tiles are done with K_j / V_j
-                    if (more) {
-                        if (x == 0) {
-                            mbar_wait(&kv_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
-                            tc_fence_after();
-                        }
-                        issue_s(x, j + 1);                              // its commit also covers the PV just issued
-                    } else {
-                        umma_commit(&o_done[x]);
-                    }
+                    issue_s(j + 1);                                      // its commit also covers the PV just issued
+                } else {
+                    umma_commit(&o_done[x]);
                 }
             }
         }
     } else {
-        const int x = (warp - 2) >> 2;                    // query tile of this softmax warp group
+        const int x = (warp - 2) >> 2;                    // query tile of this softmax warp group (warps 2-5: A, 6-9: B)
         if (x < nq) {
             const int quarter = warp & 3;
             const int row = quarter * 32 + lane;
@@ -201,7 +213,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
                 mbar_wait(&s_full[x], j & 1);
                 tc_fence_after();
-                if (j == 0) {                             // first tile: exact row max first
+                if (j == 0 && (p.dbg & 7) != 4 && (p.dbg & 7) != 2) { // first tile: exact row max first
                     float mt = -INFINITY;
 #pragma unroll 1
                     for (int col = 0; col < nk; col += 16) {
@@ -213,8 +225,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                     }
                     m_ref = mt;
                 }
+                if (j == 0 && ((p.dbg & 7) == 4 || (p.dbg & 7) == 2)) m_ref = 0.f;
                 float acc, mt;
-                softmax_pass(tS, tP, nk, c, m_ref * c, acc, mt);
+                softmax_pass(tS, tP, nk, c, m_ref * c, acc, mt, p.dbg & 7);
                 const bool need = (mt - m_ref) * c > ATT_RESCALE_LOG2;
                 if (__any_sync(0xffffffffu, need)) {
                     // rare: adopt the larger max, rescale the running sum and O (S_j complete implies PV_{j-1} complete
@@ -276,6 +289,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
 
 using namespace b200x;
 
+static int g_attn_dbg = 0;
+// diagnostic only (not part of the public header): select a stripped-down variant of the kernel for bottleneck analysis
+extern "C" void b200x_debug_attention_variant(int v) { g_attn_dbg = v; }
+
 extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int head_dim,
                                void* stream) {
     B200X_REQUIRE(head_dim == ATT_HD, "attention: head_dim %d unsupported (kernel is specialised for 64)", head_dim);
@@ -292,7 +309,7 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     const uint64_t strides[2] = {static_cast<uint64_t>(width) * 2, static_cast<uint64_t>(width) * 2 * tokens};
     const uint32_t box[3] = {ATT_HD, ATT_TILE, 1};
     B200X_TRY(make_tmap_bf16(&tm, d_qkv, 3, dims, strides, box));
-    AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f};
+    AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_dbg};
     dim3 grid(ceil_div(tokens, 2 * ATT_TILE), heads, copies);
     attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
     B200X_CUDA_TRY(cudaGetLastError());

@@ -64,6 +64,12 @@ def gemm(a, lda, w, ldw, m, n, k, bn, out, ldc, mode, bias, gelu, resid):
 
 
 print(f"copies={copies}  M={M}")
+if os.environ.get("KB_ATTN_VARIANTS"):
+    import ctypes
+    for v in (0, 4, 4 + 8, 4 + 16, 4 + 8 + 16):
+        lib.b200x_debug_attention_variant(ctypes.c_int(v))
+        timeit(lambda: _lib.check(lib.b200x_attention(P(qkv), P(att), copies, T, H, 64, P(None))), flops=4 * copies * H * T * T * 64, name=f"attention variant {v}")
+    sys.exit(0)
 total += timeit(lambda: _lib.check(lib.b200x_layernorm(P(x), M, D, P(gam), P(bet), P(None), P(None), 0, 0, 1e-5, P(h), P(None), P(None))),
                 bytes_=M * D * 6, name="layernorm fp32->bf16") * 2
 total += timeit(lambda: gemm(h, D, w_qkv, D, M, 3 * D, D, 192, qkv, 3 * D, 0, None, 0, None), flops=2 * M * D * 3 * D, name="gemm qkv   N=1152 K=384  bf16")
