@@ -34,7 +34,6 @@ struct AttnParams {
     int heads;
     __nv_bfloat16* out;   // [copies * tokens, heads * 64]
     float scale_log2;     // (1/sqrt(64)) * log2(e)
-    int dbg;              // diagnostic variants (0 = normal): 1 no MUFU, 2 no S loads, 3 no P stores, 4 no softmax work
 };
 
 // 32 (or, for a tail chunk, 16) scores -> p = 2^(s*c - m_ref*c) -> packed bf16 in TMEM; accumulates the row sum / tile max.
@@ -92,6 +91,7 @@ __device__ __forceinline__ void softmax_pass(uint32_t tS, uint32_t tP, int nk, f
     }
 }
 
+template <int DBG>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -164,15 +164,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
                 const uint32_t idesc_s = make_idesc_bf16(ATT_TILE, nk, false);
                 const uint64_t kd = k_desc0 + static_cast<uint64_t>((j % ATT_KV_STAGES) * (ATT_TILE_BYTES >> 4));
+                if (!(DBG & 16))
 #pragma unroll
-                if (!(p.dbg & 16))
                 for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, q_desc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
                 umma_commit(&s_full[x]);
             };
             auto issue_pv = [&](int j) {                  // O_x += P_x V_j
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
                 const uint64_t vd = v_desc0 + static_cast<uint64_t>((j % ATT_KV_STAGES) * (ATT_TILE_BYTES >> 4));
-                if (p.dbg & 8) return;
+                if (DBG & 8) return;
                 if (nk == ATT_TILE) {
 #pragma unroll
                     for (int ks = 0; ks < ATT_TILE / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
@@ -213,7 +213,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
                 mbar_wait(&s_full[x], j & 1);
                 tc_fence_after();
-                if (j == 0 && (p.dbg & 7) != 4 && (p.dbg & 7) != 2) { // first tile: exact row max first
+                if (j == 0 && (DBG & 7) != 4 && (DBG & 7) != 2) { // first tile: exact row max first
                     float mt = -INFINITY;
 #pragma unroll 1
                     for (int col = 0; col < nk; col += 16) {
@@ -225,9 +225,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                     }
                     m_ref = mt;
                 }
-                if (j == 0 && ((p.dbg & 7) == 4 || (p.dbg & 7) == 2)) m_ref = 0.f;
+                if (j == 0 && ((DBG & 7) == 4 || (DBG & 7) == 2)) m_ref = 0.f;
                 float acc, mt;
-                softmax_pass(tS, tP, nk, c, m_ref * c, acc, mt, p.dbg & 7);
+                softmax_pass(tS, tP, nk, c, m_ref * c, acc, mt, DBG & 7);
                 const bool need = (mt - m_ref) * c > ATT_RESCALE_LOG2;
                 if (__any_sync(0xffffffffu, need)) {
                     // rare: adopt the larger max, rescale the running sum and O (S_j complete implies PV_{j-1} complete
@@ -290,6 +290,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
 using namespace b200x;
 
 static int g_attn_dbg = 0;
+
+template <int DBG>
+static int launch_attention(const CUtensorMap& tm, const AttnParams& p, dim3 grid, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        configured = true;
+    }
+    attention_kernel<DBG><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
 // diagnostic only (not part of the public header): select a stripped-down variant of the kernel for bottleneck analysis
 extern "C" void b200x_debug_attention_variant(int v) { g_attn_dbg = v; }
 
@@ -298,20 +311,24 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     B200X_REQUIRE(head_dim == ATT_HD, "attention: head_dim %d unsupported (kernel is specialised for 64)", head_dim);
     B200X_REQUIRE(copies > 0 && tokens > 0 && heads > 0, "attention: empty problem");
     B200X_REQUIRE(tokens % 16 == 0, "attention: tokens=%d must be a multiple of 16", tokens);
-    static bool configured = false;
-    if (!configured) {
-        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        configured = true;
-    }
     const int width = 3 * heads * ATT_HD;
     CUtensorMap tm;
     const uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(tokens), static_cast<uint64_t>(copies)};
     const uint64_t strides[2] = {static_cast<uint64_t>(width) * 2, static_cast<uint64_t>(width) * 2 * tokens};
     const uint32_t box[3] = {ATT_HD, ATT_TILE, 1};
     B200X_TRY(make_tmap_bf16(&tm, d_qkv, 3, dims, strides, box));
-    AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_dbg};
+    AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f};
     dim3 grid(ceil_div(tokens, 2 * ATT_TILE), heads, copies);
-    attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
-    B200X_CUDA_TRY(cudaGetLastError());
-    return B200X_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (g_attn_dbg) {
+        case 0: return launch_attention<0>(tm, p, grid, s);
+        case 4: return launch_attention<4>(tm, p, grid, s);
+        case 12: return launch_attention<12>(tm, p, grid, s);
+        case 20: return launch_attention<20>(tm, p, grid, s);
+        case 28: return launch_attention<28>(tm, p, grid, s);
+        case 1: return launch_attention<1>(tm, p, grid, s);
+        case 2: return launch_attention<2>(tm, p, grid, s);
+        case 3: return launch_attention<3>(tm, p, grid, s);
+        default: return set_error(B200X_ERR_INVALID, "attention: unknown diagnostic variant %d", g_attn_dbg);
+    }
 }
