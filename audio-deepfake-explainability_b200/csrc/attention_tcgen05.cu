@@ -19,7 +19,10 @@
 
 namespace b200x {
 
-constexpr int ATT_THREADS = 352;       // warp 0 TMA, 1 MMA(A), 2-5 softmax(A), 6-9 softmax(B), 10 MMA(B)
+constexpr int ATT_THREADS = 352;       // warps 0-3 softmax(A), 4-7 softmax(B), 8 TMA, 9 MMA(A), 10 MMA(B)
+// The producer / issuer roles sit on the HIGHEST warp ids: the SM's warp arbiter prefers higher ids, and an issuer that
+// loses its issue slots to the softmax warps delays every tcgen05.mma by hundreds of cycles.
+constexpr int ATT_W_TMA = 8, ATT_W_MMA = 9;
 constexpr int ATT_TILE = 128;
 constexpr int ATT_HD = 64;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_HD * 2;     // 16 KB
@@ -28,68 +31,50 @@ constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 + 2 * ATT_KV_STAGES) + 256 + 1024;
 constexpr uint32_t ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_S_COL = 0, ATT_O_COL = 256, ATT_P_COL = 384;
 constexpr float ATT_RESCALE_LOG2 = 8.0f;
+#ifndef ATT_ALTERNATE
+#define ATT_ALTERNATE 0
+#endif
 
 struct AttnParams {
     int tokens;        // tokens per copy (multiple of 16)
     int heads;
     __nv_bfloat16* out;   // [copies * tokens, heads * 64]
     float scale_log2;     // (1/sqrt(64)) * log2(e)
+    long long* prof;      // diagnostic variant 32: [cta][11 warps][4] cycle counters (else unused)
+    float zero;           // always 0.0f: an operand ptxas cannot fold (see exp_chunk)
 };
 
-// 32 (or, for a tail chunk, 16) scores -> p = 2^(s*c - m_ref*c) -> packed bf16 in TMEM; accumulates the row sum / tile max.
-// The fp32 -> bf16 conversion is a byte permute that keeps the high halves (truncation) instead of F2FP: the conversion
-// unit shares the MUFU pipe, which is what bounds this kernel.  The row sum is taken over the TRUNCATED values, so the
-// softmax weights stay exactly normalised and carry the same error variance as round-to-nearest, without bias.
-__device__ __forceinline__ void softmax_chunk(const uint32_t (&r)[32], bool wide, uint32_t tP_col, float c, float mc,
-                                              float& acc, float& mt, int dbg = 0) {
-    uint32_t pk[16];
+// 32 scores (registers r[0..32)) -> p = 2^(s*c - m_ref*c) -> bf16 pairs (round to nearest) -> 16 TMEM columns of P.
+// Packed fp32x2 math keeps the issue cost at 2.5 slots per score: 1/2 FFMA2, MUFU, 1/2 F2FP, 1/2 FADD2.
+// Scheduling: with the whole row in registers ptxas would hoist all 64 FFMA2 and then emit the MUFUs in one long run,
+// which blocks the (in-order) warp on the MUFU queue while its other work waits.  The two 16-score halves of a chunk
+// therefore take their addend from `link` = fma(sum two halves back, 0, -m*c): a true data dependence on older results
+// (value unchanged) that keeps at most two halves in flight, so MUFU runs stay short and interleave with FMA work.
+template <int DBG>
+__device__ __forceinline__ void exp_chunk(const uint32_t* r, uint32_t (&pk)[16], uint64_t c2, uint64_t nmc2, uint64_t zero2,
+                                          uint64_t& acc_a, uint64_t& acc_b) {
+    const uint64_t link_a = ffma2(acc_a, zero2, nmc2);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        uint32_t b0 = 0u, b1 = 0u;
-        if (wide || i < 8) {
-            const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
-            mt = fmax3(mt, s0, s1);
-            if (dbg == 1) {
-                b0 = __float_as_uint(fmaf(s0, c, -mc)) & 0xFFFF0000u;
-                b1 = __float_as_uint(fmaf(s1, c, -mc)) & 0xFFFF0000u;
-            } else {
-                b0 = __float_as_uint(ex2_approx(fmaf(s0, c, -mc))) & 0xFFFF0000u;
-                b1 = __float_as_uint(ex2_approx(fmaf(s1, c, -mc))) & 0xFFFF0000u;
-            }
-        }
-        acc += __uint_as_float(b0) + __uint_as_float(b1);
-        pk[i] = __byte_perm(b0, b1, 0x7632);      // low half = bf16(s0), high half = bf16(s1)
+    for (int i = 0; i < 8; ++i) {
+        float x0, x1;
+        unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, link_a), x0, x1);
+        const float p0 = (DBG & 1) ? x0 : ex2_approx(x0), p1 = (DBG & 1) ? x1 : ex2_approx(x1);
+        acc_a = fadd2(acc_a, pack_f32x2(p0, p1));
+        pk[i] = pack_bf16(p0, p1);
     }
-    if (dbg != 3) tmem_st16(tP_col, pk);       // a 16-column tail chunk stores 8 meaningful + 8 zero words (never read)
+    const uint64_t link_b = ffma2(acc_b, zero2, nmc2);
+#pragma unroll
+    for (int i = 8; i < 16; ++i) {
+        float x0, x1;
+        unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, link_b), x0, x1);
+        const float p0 = (DBG & 1) ? x0 : ex2_approx(x0), p1 = (DBG & 1) ? x1 : ex2_approx(x1);
+        acc_b = fadd2(acc_b, pack_f32x2(p0, p1));
+        pk[i] = pack_bf16(p0, p1);
+    }
 }
 
-// One streaming pass over a score tile.  The TMEM load of chunk i+1 is in flight while chunk i is exponentiated
-// (two register buffers; a buffer is only read after the tcgen05.wait::ld that follows its load).
-__device__ __forceinline__ void softmax_pass(uint32_t tS, uint32_t tP, int nk, float c, float mc, float& acc, float& mt, int dbg = 0) {
-    acc = 0.f;
-    mt = -INFINITY;
-    if (dbg == 4) { acc = 1.f; mt = mc / c; return; }
-    uint32_t ra[32], rb[32];
-    if (dbg == 2) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ra[i] = rb[i] = __float_as_uint(mc / c - 0.001f * i);
-    }
-    if (dbg != 2) { if (nk >= 32) tmem_ld32(tS, ra); else tmem_ld16(tS, ra); }
-#pragma unroll
-    for (int ci = 0; ci < ATT_TILE / 32; ++ci) {
-        const int col = ci * 32;
-        if (col < nk) {
-            tmem_wait_ld();
-            const int nxt = col + 32;
-            if (nxt < nk && dbg != 2) {
-                if ((ci & 1) == 0) { if (nxt + 32 <= nk) tmem_ld32(tS + nxt, rb); else tmem_ld16(tS + nxt, rb); }
-                else               { if (nxt + 32 <= nk) tmem_ld32(tS + nxt, ra); else tmem_ld16(tS + nxt, ra); }
-            }
-            if ((ci & 1) == 0) softmax_chunk(ra, col + 32 <= nk, tP + col / 2, c, mc, acc, mt, dbg);
-            else               softmax_chunk(rb, col + 32 <= nk, tP + col / 2, c, mc, acc, mt, dbg);
-        }
-    }
-}
+// diagnostic variant 32: CTA (0,0,0) appends (event << 56 | step << 48 | clock) records per warp behind the counters
+#define ATT_TRACE(ev, step) do { if (DBG == 32 && trace != nullptr && tr_n < 120) { trace[tr_n++] = (static_cast<long long>(ev) << 56) | (static_cast<long long>(step) << 48) | (clock64() & 0xFFFFFFFFFFFFll); } } while (0)
 
 template <int DBG>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -103,10 +88,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     uint64_t* q_full = bars;
     uint64_t* kv_full = bars + 1;
     uint64_t* kv_empty = kv_full + ATT_KV_STAGES;
-    uint64_t* s_full = kv_empty + ATT_KV_STAGES;          // [2]
-    uint64_t* p_ready = s_full + 2;                       // [2]
-    uint64_t* o_done = p_ready + 2;                       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+    uint64_t* s_full = kv_empty + ATT_KV_STAGES;          // [2] S_x(j) is in TMEM
+    uint64_t* s_free = s_full + 2;                        // [2] softmax x holds S_x(j) in registers: S_x(j+1) may be issued
+    uint64_t* p_ready = s_free + 2;                       // [2] P_x(j) is in TMEM
+    uint64_t* pv_done = p_ready + 2;                      // [2] O_x += P_x(j) V_j has retired
+    uint64_t* turn = pv_done + 2;                         // [2] MUFU hand-over between the two softmax groups
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(turn + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -115,8 +102,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     const int nq = (q0 + ATT_TILE < p.tokens) ? 2 : 1;    // query tiles of this block that hold valid rows
     const int nkv = (p.tokens + ATT_TILE - 1) / ATT_TILE;
     const int hidden = p.heads * ATT_HD;
+    long long* prof = nullptr;
+    if (DBG == 32) prof = p.prof + ((static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 44 + warp * 4;
+    long long* trace = nullptr;
+    int tr_n = 0;
+    if (DBG == 32 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0)
+        trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * 44 + warp * 128;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == ATT_W_TMA && elect_one()) {
         tma_prefetch_desc(&tmQKV);
         mbar_init(q_full, 1);
         for (int s = 0; s < ATT_KV_STAGES; ++s) {
@@ -125,19 +118,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
         }
         for (int x = 0; x < 2; ++x) {
             mbar_init(&s_full[x], 1);
+            mbar_init(&s_free[x], 4);
             mbar_init(&p_ready[x], 4);
-            mbar_init(&o_done[x], 1);
+            mbar_init(&pv_done[x], 1);
+            mbar_init(&turn[x], 4);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
+    if (warp == ATT_W_MMA) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {
+    if (warp == ATT_W_TMA) {
+        if (elect_one()) {          // elect.sync: ptxas emits straight-line UTMALDG / UTCHMMA (no per-lane BRA.U.ANY loop)
+            if (DBG == 32 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)
+                trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * 44 + warp * 128;
+            ATT_TRACE(0, 0);
             mbar_expect_tx(q_full, nq * ATT_TILE_BYTES);
             tma_load_3d(sQ, &tmQKV, q_full, head * ATT_HD, q0, copy);
             if (nq == 2) tma_load_3d(sQ + ATT_TILE_BYTES, &tmQKV, q_full, head * ATT_HD, q0 + ATT_TILE, copy);
@@ -145,14 +143,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 const int st = j % ATT_KV_STAGES;
                 const uint32_t ph = (j / ATT_KV_STAGES) & 1;
                 mbar_wait(&kv_empty[st], ph ^ 1);
+                ATT_TRACE(1, j);
                 mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
                 tma_load_3d(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], hidden + head * ATT_HD, j * ATT_TILE, copy);
                 tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * hidden + head * ATT_HD, j * ATT_TILE, copy);
             }
         }
-    } else if (warp == 1 || warp == 10) {
-        const int x = (warp == 1) ? 0 : 1;                // query tile served by this issuer
-        if (lane == 0 && x < nq) {
+    } else if (warp >= ATT_W_MMA) {
+        // one issuer per query tile: the tiles' chains (S -> registers -> next S;  P -> P.V) stay independent of each other
+        const int x = warp - ATT_W_MMA;
+        if (x < nq && elect_one()) {
+            if (DBG == 32 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)
+                trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * 44 + warp * 128;
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_TILE, ATT_HD, true);
             const uint32_t tS = tmem_base + ATT_S_COL + x * ATT_TILE;
             const uint32_t tO = tmem_base + ATT_O_COL + x * ATT_HD;
@@ -164,42 +166,55 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
                 const uint32_t idesc_s = make_idesc_bf16(ATT_TILE, nk, false);
                 const uint64_t kd = k_desc0 + static_cast<uint64_t>((j % ATT_KV_STAGES) * (ATT_TILE_BYTES >> 4));
-                if (!(DBG & 16))
+                if (!(DBG & 16)) {
 #pragma unroll
-                for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, q_desc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, q_desc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                }
                 umma_commit(&s_full[x]);
             };
             auto issue_pv = [&](int j) {                  // O_x += P_x V_j
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
                 const uint64_t vd = v_desc0 + static_cast<uint64_t>((j % ATT_KV_STAGES) * (ATT_TILE_BYTES >> 4));
-                if (DBG & 8) return;
-                if (nk == ATT_TILE) {
+                if (!(DBG & 8)) {
+                    if (nk == ATT_TILE) {
 #pragma unroll
-                    for (int ks = 0; ks < ATT_TILE / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
-                } else {
-                    for (int ks = 0; ks < nk / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                        for (int ks = 0; ks < ATT_TILE / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                    } else {
+                        for (int ks = 0; ks < nk / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                    }
                 }
+                umma_commit(&pv_done[x]);
+                umma_commit(&kv_empty[j % ATT_KV_STAGES]);              // this tile is done with K_j / V_j
             };
+            long long pc_kv = 0, pc_p = 0, pc_f = 0, pc_t = 0, pc_start = 0;
+            if (DBG == 32) pc_start = clock64();
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
             tc_fence_after();
             issue_s(0);
             for (int j = 0; j < nkv; ++j) {
+                if (j + 1 < nkv) {
+                    if (DBG == 32) pc_t = clock64();
+                    mbar_wait(&kv_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
+                    if (DBG == 32) { const long long t = clock64(); pc_kv += t - pc_t; pc_t = t; }
+                    ATT_TRACE(1, j);
+                    mbar_wait(&s_free[x], j & 1);                       // S_x(j) sits in the softmax warps' registers
+                    tc_fence_after();
+                    if (DBG == 32) pc_f += clock64() - pc_t;
+                    ATT_TRACE(2, j);
+                    issue_s(j + 1);
+                }
+                if (DBG == 32) pc_t = clock64();
                 mbar_wait(&p_ready[x], j & 1);
                 tc_fence_after();
+                if (DBG == 32) pc_p += clock64() - pc_t;
+                ATT_TRACE(3, j);
                 issue_pv(j);
-                umma_commit(&kv_empty[j % ATT_KV_STAGES]);              // this tile is done with K_j / V_j
-                if (j + 1 < nkv) {
-                    mbar_wait(&kv_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
-                    tc_fence_after();
-                    issue_s(j + 1);                                      // its commit also covers the PV just issued
-                } else {
-                    umma_commit(&o_done[x]);
-                }
             }
+            if (DBG == 32) { prof[0] = pc_kv; prof[1] = pc_p; prof[2] = clock64() - pc_start; prof[3] = pc_f; }
         }
     } else {
-        const int x = (warp - 2) >> 2;                    // query tile of this softmax warp group (warps 2-5: A, 6-9: B)
+        const int x = warp >> 2;                          // query tile of this softmax warp group (warps 0-3: A, 4-7: B)
         if (x < nq) {
             const int quarter = warp & 3;
             const int row = quarter * 32 + lane;
@@ -208,34 +223,63 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
             const uint32_t tO = t_lane + ATT_O_COL + x * ATT_HD;
             const uint32_t tP = t_lane + ATT_P_COL + x * ATT_HD;
             const float c = p.scale_log2;
-            float m_ref = -INFINITY, l_sum = 0.f;
+            const uint64_t c2 = pack_f32x2(c, c);
+            const uint64_t zero2 = pack_f32x2(p.zero, p.zero);
+            float m_ref = -INFINITY;
+            uint64_t l2 = 0ull, l2b = 0ull;               // running row sum, four partial sums
+            long long pc_wait = 0, pc_pass = 0, pc_tail = 0, pc_t = 0, pc_ld = 0, pc_max = 0, pc_pv = 0, pc_u = 0;
             for (int j = 0; j < nkv; ++j) {
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
+                if (DBG == 32) pc_t = clock64();
                 mbar_wait(&s_full[x], j & 1);
                 tc_fence_after();
-                if (j == 0 && (DBG & 7) != 4 && (DBG & 7) != 2) { // first tile: exact row max first
-                    float mt = -INFINITY;
-#pragma unroll 1
-                    for (int col = 0; col < nk; col += 16) {
-                        uint32_t r[16];
-                        tmem_ld16(tS + col, r);
-                        tmem_wait_ld();
+                if (DBG == 32) { const long long t = clock64(); pc_wait += t - pc_t; pc_t = t; }
+                ATT_TRACE(1, j);
+                // the whole score row into registers, then hand the S buffer back to the tensor pipe at once
+                uint32_t r[ATT_TILE];
+                if ((DBG & 7) != 4) {
+                    if (nk == ATT_TILE) {
+                        tmem_ld32(tS, r); tmem_ld32(tS + 32, r + 32); tmem_ld32(tS + 64, r + 64); tmem_ld32(tS + 96, r + 96);
+                    } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) mt = fmaxf(mt, __uint_as_float(r[i]));
+                        for (int col = 0; col < ATT_TILE; col += 16) {
+                            if (col < nk) {
+                                tmem_ld16(tS + col, r + col);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) r[col + i] = 0xff800000u;   // -inf: exp2 -> 0, never read by P.V
+                            }
+                        }
                     }
-                    m_ref = mt;
+                    tmem_wait_ld();
                 }
-                if (j == 0 && ((DBG & 7) == 4 || (DBG & 7) == 2)) m_ref = 0.f;
-                float acc, mt;
-                softmax_pass(tS, tP, nk, c, m_ref * c, acc, mt, DBG & 7);
-                const bool need = (mt - m_ref) * c > ATT_RESCALE_LOG2;
-                if (__any_sync(0xffffffffu, need)) {
-                    // rare: adopt the larger max, rescale the running sum and O (S_j complete implies PV_{j-1} complete
-                    // on the in-order tensor pipe, so O is quiescent), then redo the tile against the new reference.
-                    const float m_new = fmaxf(m_ref, mt);
-                    const float sc = ex2_approx((m_ref - m_new) * c);
-                    l_sum *= sc;
-                    if (j > 0) {
+                if (DBG == 32) { pc_u = clock64(); pc_ld += pc_u - pc_t; }
+                ATT_TRACE(2, j);
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&s_free[x]);
+                if ((DBG & 7) != 4) {
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < ATT_TILE; i += 8) {
+                        m0 = fmax3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                        m1 = fmax3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                        m2 = fmax3(m2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+                        m3 = fmax3(m3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+                    }
+                    const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    if (j == 0) m_ref = mt;
+                    if (DBG == 32) { const long long t = clock64(); pc_max += t - pc_u; pc_u = t; }
+                    ATT_TRACE(3, j);
+                    // lazy rescaling: the reference max is replaced (and O, l rescaled) only when this tile exceeds it by 2^8
+                    const bool need = (mt - m_ref) * c > ATT_RESCALE_LOG2;
+                    bool pv_waited = false;
+                    if (__any_sync(0xffffffffu, need)) {
+                        if (j > 0) { mbar_wait(&pv_done[x], (j - 1) & 1); tc_fence_after(); pv_waited = true; }   // O_x is quiescent
+                        const float m_new = fmaxf(m_ref, mt);
+                        const float sc = ex2_approx((m_ref - m_new) * c);
+                        l2 = ffma2(l2, pack_f32x2(sc, sc), 0ull);
+                        l2b = ffma2(l2b, pack_f32x2(sc, sc), 0ull);
 #pragma unroll
                         for (int cidx = 0; cidx < ATT_HD; cidx += 16) {
                             uint32_t o[16];
@@ -245,20 +289,58 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
                             tmem_st16(tO + cidx, o);
                         }
+                        m_ref = m_new;
                     }
-                    m_ref = m_new;
-                    softmax_pass(tS, tP, nk, c, m_ref * c, acc, mt);
+                    const float mc = m_ref * c;
+                    const uint64_t nmc2 = pack_f32x2(-mc, -mc);
+                    // one-time stagger: tile B starts its first exponential phase when tile A has finished its own, so that
+                    // from then on one group's load / max / wait phases fall into the other group's MUFU phase
+                    // strict alternation of the exponential phases (both tiles valid): group x runs its MUFU phase j after
+                    // the other group has finished its phase j (x = 1) / j - 1 (x = 0)
+                    if (ATT_ALTERNATE && nq == 2) {
+                        if (x == 1) mbar_wait(&turn[0], j & 1);
+                        else if (j > 0) mbar_wait(&turn[1], (j - 1) & 1);
+                    }
+                    uint32_t pk[16];
+                    exp_chunk<DBG>(r, pk, c2, nmc2, zero2, l2, l2b);
+                    if (DBG == 32) pc_u = clock64();
+                    // P_x may only be overwritten once P_x(j-1) . V has retired (checked here, a quarter of the pass later)
+                    if (j > 0 && !pv_waited) { mbar_wait(&pv_done[x], (j - 1) & 1); tc_fence_after(); }
+                    if (DBG == 32) pc_pv += clock64() - pc_u;
+                    ATT_TRACE(4, j);
+                    if (DBG == 32 && j + 1 < nkv) { const bool rdy = mbar_try_wait(&s_full[x], (j + 1) & 1); ATT_TRACE(rdy ? 8 : 7, j); }
+                    tmem_st16(tP, pk);
+                    exp_chunk<DBG>(r + 32, pk, c2, nmc2, zero2, l2, l2b);
+                    tmem_st16(tP + 16, pk);
+                    exp_chunk<DBG>(r + 64, pk, c2, nmc2, zero2, l2, l2b);
+                    tmem_st16(tP + 32, pk);
+                    exp_chunk<DBG>(r + 96, pk, c2, nmc2, zero2, l2, l2b);
+                    tmem_st16(tP + 48, pk);
+                    if (ATT_ALTERNATE && nq == 2) {
+                        __syncwarp();
+                        if (elect_one()) mbar_arrive(&turn[x]);
+                    }
+                } else {
+                    if (j > 0) { mbar_wait(&pv_done[x], (j - 1) & 1); tc_fence_after(); }
+                    l2 = pack_f32x2(1.f, 0.f);
                 }
-                l_sum += acc;
+                if (DBG == 32) { const long long t = clock64(); pc_pass += t - pc_t; pc_t = t; }
+                ATT_TRACE(5, j);
+                if (DBG == 32 && j + 1 < nkv) { const bool rdy = mbar_try_wait(&s_full[x], (j + 1) & 1); ATT_TRACE(rdy ? 10 : 9, j); }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_ready[x]);
+                if (elect_one()) mbar_arrive(&p_ready[x]);
+                if (DBG == 32) { const long long t = clock64(); pc_tail += t - pc_t; pc_t = t; }
+                ATT_TRACE(6, j);
             }
-            mbar_wait(&o_done[x], 0);
+            if (DBG == 32 && lane == 0) { prof[0] = pc_wait; prof[1] = pc_pass; prof[2] = pc_tail; prof[3] = (pc_ld << 42) | (pc_max << 21) | pc_pv; }
+            mbar_wait(&pv_done[x], (nkv - 1) & 1);
             tc_fence_after();
             const int q = q0 + x * ATT_TILE + row;
-            const float inv = 1.0f / l_sum;
+            float la, lb;
+            unpack_f32x2(fadd2(l2, l2b), la, lb);
+            const float inv = 1.0f / (la + lb);
             uint4 packed[8];
 #pragma unroll
             for (int cidx = 0; cidx < ATT_HD; cidx += 16) {
@@ -282,7 +364,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
+    if (warp == ATT_W_MMA) tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
 }
 
 }  // namespace b200x
@@ -304,7 +386,10 @@ static int launch_attention(const CUtensorMap& tm, const AttnParams& p, dim3 gri
 }
 
 // diagnostic only (not part of the public header): select a stripped-down variant of the kernel for bottleneck analysis
+static long long* g_attn_prof = nullptr;
 extern "C" void b200x_debug_attention_variant(int v) { g_attn_dbg = v; }
+// diagnostic variant 32 writes per-CTA cycle counters ([cta][10][4] long long) to this device buffer
+extern "C" void b200x_debug_attention_profile(void* d_buf) { g_attn_prof = static_cast<long long*>(d_buf); }
 
 extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int head_dim,
                                void* stream) {
@@ -317,7 +402,7 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     const uint64_t strides[2] = {static_cast<uint64_t>(width) * 2, static_cast<uint64_t>(width) * 2 * tokens};
     const uint32_t box[3] = {ATT_HD, ATT_TILE, 1};
     B200X_TRY(make_tmap_bf16(&tm, d_qkv, 3, dims, strides, box));
-    AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f};
+    AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_prof, 0.0f};
     dim3 grid(ceil_div(tokens, 2 * ATT_TILE), heads, copies);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (g_attn_dbg) {
@@ -327,8 +412,7 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
         case 20: return launch_attention<20>(tm, p, grid, s);
         case 28: return launch_attention<28>(tm, p, grid, s);
         case 1: return launch_attention<1>(tm, p, grid, s);
-        case 2: return launch_attention<2>(tm, p, grid, s);
-        case 3: return launch_attention<3>(tm, p, grid, s);
+        case 32: return launch_attention<32>(tm, p, grid, s);
         default: return set_error(B200X_ERR_INVALID, "attention: unknown diagnostic variant %d", g_attn_dbg);
     }
 }

@@ -41,7 +41,8 @@ struct LayerW {
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // pick the UMMA N tile that wastes the fewest padded columns (ties -> wider tile)
-int pick_block_n(int n) {
+int pick_block_n(int n, int k = 1 << 30) {
+    (void)k;
     const int cands[4] = {256, 208, 192, 128};
     int best = 128, best_waste = 1 << 30;
     for (int c : cands) {
@@ -184,14 +185,14 @@ int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* 
         LayerW& w = e->layers[l];
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n1_g.as<float>(), w.n1_b.as<float>(), nullptr, nullptr, 0, 0,
                                   c.block_ln_eps, e->h.p, nullptr, s));
-        TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
+        TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D, D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
                                   c.qkv_bias ? w.qkv_b.as<float>() : nullptr, 0, nullptr, nullptr, 0, 0, 0, s));
         TIMED(KC_ATTN, b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, s));
-        TIMED(KC_GEMM, b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
+        TIMED(KC_GEMM, b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D, D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
                                   w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
                                   c.block_ln_eps, e->h.p, nullptr, s));
-        TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
+        TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp, D), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
                                   w.fc1_b.as<float>(), 1, nullptr, nullptr, 0, 0, 0, s));
         TIMED(KC_GEMM, b200x_gemm_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, pick_block_n(D), e->x.p, D,
                                   B200X_GEMM_OUT_F32_RESID, w.fc2_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
@@ -615,11 +616,26 @@ int audio_out(b200x_engine* e, int mode, const int32_t* windows, const float* ga
         B200X_TRY(ensure_grow(e->gains, bytes));
         B200X_CUDA_TRY(cudaMemcpyAsync(e->gains.p, gains, bytes, cudaMemcpyHostToDevice, e->stream));
     }
+    // window segments: only the hops of the window's own time span are synthesised (frame range [t0, t1] -> hops t0 .. t1 + 2)
+    const bool seg_sparse = seg_stride > 0 && windows != nullptr;
+    int max_range = 0;
+    if (seg_sparse) {
+        std::vector<int32_t> rg(static_cast<size_t>(n) * 2);
+        for (int i = 0; i < n; ++i) {
+            rg[2 * i] = windows[4 * i];
+            rg[2 * i + 1] = std::max(windows[4 * i + 1], windows[4 * i] + 1);
+            max_range = std::max(max_range, rg[2 * i + 1] - rg[2 * i]);
+        }
+        B200X_TRY(ensure_grow(e->ranges, rg.size() * sizeof(int32_t)));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->ranges.p, rg.data(), rg.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));      // rg is a stack-lifetime staging buffer
+    }
     for (int c0 = 0; c0 < n; c0 += e->C) {
         const int m = std::min(e->C, n - c0);
         TIMED(KC_ISTFT, b200x_istft_masked(e->S.p, b200x_engine::s_stride, e->n_time, m, mode, windows ? e->windows.as<int32_t>() + 4 * c0 : nullptr,
                                      occ_value, gains ? e->gains.as<float>() + static_cast<size_t>(c0) * b200x_engine::n_freq : nullptr,
-                                     e->y.as<float>(), e->y_stride, nullptr, nullptr, 0, e->stream));
+                                     e->y.as<float>(), e->y_stride, nullptr, seg_sparse ? e->ranges.as<int32_t>() + 2 * c0 : nullptr,
+                                     max_range, e->stream));
         e->launches += 1;
         if (seg_stride > 0) {
             for (int i = 0; i < m; ++i) {

@@ -1,6 +1,6 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] . W[N,K]^T  (+ fused epilogue)
 //
-//   warp 0    : TMA producer (cp.async.bulk.tensor, 128B swizzle, 3-stage mbarrier ring)
+//   warp 0    : TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring; 3 stages for BN = 256)
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate in TMEM)
 //   warps 2-9 : epilogue.  TMEM lane == tile row, so tcgen05.ld hands every thread one row of the accumulator.
 //               bf16 / residual outputs: bias (+GELU) in registers, pack, st.shared into a 128B-swizzled per-warp slab
@@ -9,6 +9,10 @@
 //               token-mode outputs (tokenizer: row remap + positional encoding) take a generic coalescing path.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.  With K = 384 the epilogue is as
 // long as the MMAs, hence eight epilogue warps (two per TMEM lane quarter, splitting the column groups).
+// Pipeline depth matters more than anything else here: a ring slot cycles through "MMAs retire -> commit -> producer
+// wakes -> TMA load (L2 hit) -> issuer wakes" in ~2400 cycles while its four MMAs take ~500, so with three stages the
+// issuer waited for loads 40 % of the time (measured with the in-kernel counters, tools/gemm_profile.py).  The epilogue
+// slabs are therefore single-buffered (each warp stores at most two slabs per tile) to make room for a fourth stage.
 // Used for every dense contraction of the SpecTTTra forward (tokenizer projections, QKV, attention projection, MLP).
 #include "common.h"
 #include "ptx.cuh"
@@ -17,11 +21,11 @@ namespace b200x {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;      // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_MAX_STAGES = 4;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_SLAB_BYTES = 32 * 128;             // 32 rows x 128 bytes
-constexpr int GEMM_EPI_WARP_BYTES = 2 * GEMM_SLAB_BYTES + 1024;   // double-buffered slab (+ spare for the token path)
+constexpr int GEMM_EPI_WARP_BYTES = 5 * 1024;         // one 1024-byte-aligned slab (swizzle atom); the token path stages 32 x 36 floats
 
 struct GemmParams {
     int M, N, K;
@@ -32,6 +36,7 @@ struct GemmParams {
     int act_gelu;
     const float* pe;      // fp32 [group_in, N] (OUT_F32_TOKEN) or null
     int group_in, group_out, group_off;   // out_row = (m / group_in) * group_out + group_off + m % group_in
+    long long* prof;      // diagnostic (usually null): per CTA {issuer wait on loads, wait on epilogue, issuer total, tiles}
 };
 
 template <int BN>
@@ -39,7 +44,8 @@ struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_OFFSET = GEMM_STAGES * STAGE_BYTES;
+    static constexpr int STAGES = (GEMM_MAX_STAGES * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_WARP_BYTES + 1280 <= 232448) ? GEMM_MAX_STAGES : 3;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int EPI_BYTES = GEMM_EPI_WARPS * GEMM_EPI_WARP_BYTES;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
@@ -84,11 +90,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCtail, GemmParams p) {
     using L = GemmSmem<BN>;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    constexpr int STAGES = L::STAGES;
     extern __shared__ uint8_t smem_raw[];
+    long long gt_start = 0;
+    if (p.prof != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_start));
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-    uint64_t* empty_bar = full_bar + GEMM_STAGES;
-    uint64_t* tfull_bar = empty_bar + GEMM_STAGES;
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -99,11 +108,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
-        for (int s = 0; s < GEMM_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
@@ -121,7 +130,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {          // elect.sync: ptxas emits straight-line UTMALDG / UTCHMMA (no per-lane BRA.U.ANY loop)
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -132,25 +141,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                     tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
                     tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
-                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {          // elect.sync: ptxas emits straight-line UTMALDG / UTCHMMA (no per-lane BRA.U.ANY loop)
             constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, false);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
+            long long pc_full = 0, pc_te = 0, pc_t = 0, pc_tiles = 0;
+            const long long pc_start = p.prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                if (p.prof) pc_t = clock64();
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
+                if (p.prof) { pc_te += clock64() - pc_t; ++pc_tiles; }
                 const uint32_t d_tmem = tmem_base + as * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    if (p.prof) pc_t = clock64();
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (p.prof) pc_full += clock64() - pc_t;
                     const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
                     const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
@@ -160,10 +175,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);      // frees the smem slot once these MMAs retire
-                    if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[as]);             // accumulator ready for the epilogue
                 if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (p.prof) {
+                long long* o = p.prof + blockIdx.x * 8;
+                o[0] = pc_full; o[1] = pc_te; o[2] = clock64() - pc_start; o[3] = pc_tiles;
             }
         }
     } else {
@@ -171,7 +190,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter + 32)
         const int half = (warp - 2) >> 2;                // which of the two warps sharing this lane quarter
         uint8_t* slab = smem + L::EPI_OFFSET + (warp - 2) * GEMM_EPI_WARP_BYTES;
-        int buf = 0;
         int as = 0;
         uint32_t aphase = 0;
         const int sw = lane & 7;                         // 128B-swizzle phase of this thread's slab row
@@ -189,9 +207,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int c = g * 64;
                     const int n0 = n_blk * BN + c;
                     const bool full = (c + 64 <= BN);
-                    if (lane == 0) bulk_wait_read<1>();          // the store that last used this buffer has read it
+                    bulk_wait_read<0>();                         // the store that last used this slab has read it
                     __syncwarp();
-                    uint8_t* dst = slab + buf * GEMM_SLAB_BYTES;
+                    uint8_t* dst = slab;
                     if (full) {
                         uint32_t r[64];
                         tmem_ld32(t_row + c, r);
@@ -232,11 +250,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && m_warp < p.M && n0 < p.N) {
+                    if (m_warp < p.M && n0 < p.N && elect_one()) {
                         tma_store_2d(full ? &tmC : &tmCtail, dst, n0, m_warp);   // rows >= M / cols >= N are clipped by TMA
                         bulk_commit();
                     }
-                    buf ^= 1;
                 }
             } else if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
                 // column groups of 32 fp32 (128 bytes per thread row); x += acc + bias via TMA reduce-add
@@ -245,9 +262,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int g = half; g < NG; g += 2) {
                     const int c = g * 32;
                     const int n0 = n_blk * BN + c;
-                    if (lane == 0) bulk_wait_read<1>();
+                    bulk_wait_read<0>();
                     __syncwarp();
-                    uint8_t* dst = slab + buf * GEMM_SLAB_BYTES;
+                    uint8_t* dst = slab;
                     uint32_t r[32];
                     tmem_ld32(t_row + c, r);
                     tmem_wait_ld();
@@ -261,16 +278,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0 && m_warp < p.M && n0 < p.N) {
+                    if (m_warp < p.M && n0 < p.N && elect_one()) {
                         tma_reduce_add_2d(&tmC, dst, n0, m_warp);
                         bulk_commit();
                     }
-                    buf ^= 1;
                 }
             } else {
                 // token mode: generic transposing path (row remap + positional encoding), 32-column chunks
                 float* stage = reinterpret_cast<float*>(slab);
-                if (lane == 0) bulk_wait_read<0>();
+                bulk_wait_read<0>();
                 __syncwarp();
                 constexpr int NCHUNK = (BN + 31) / 32;
 #pragma unroll 1
@@ -297,15 +313,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (elect_one()) mbar_arrive(&tempty_bar[as]);
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
-        if (lane == 0) bulk_wait<0>();                   // all tensor stores of this warp have completed
+        bulk_wait<0>();                   // all tensor stores of this warp have completed
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (p.prof != nullptr && threadIdx.x == 0) {
+        long long gt_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+        p.prof[blockIdx.x * 8 + 4] = gt_start;
+        p.prof[blockIdx.x * 8 + 5] = gt_end;
+    }
 }
 
 static int g_num_sms = 0;
@@ -334,6 +356,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }  // namespace b200x
 
 using namespace b200x;
+
+static long long* g_gemm_prof = nullptr;
+// diagnostic only (not part of the public header): device buffer of 4 long long per CTA for the issuer's cycle counters
+extern "C" void b200x_debug_gemm_profile(void* d_buf) { g_gemm_prof = static_cast<long long*>(d_buf); }
+extern "C" void b200x_debug_gemm_bres(int) {}
 
 extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n,
                                void* d_out, int ldc, int out_mode, const float* d_bias, int act_gelu,
@@ -374,7 +401,7 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
         tmC = tmA;            // unused in token mode
         tmCtail = tmA;
     }
-    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off};
+    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off, g_gemm_prof};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (block_n) {
         case 128: return launch_gemm<128>(tmA, tmB, tmC, tmCtail, p, s);

@@ -1,7 +1,9 @@
 // Library-wide runtime pieces of the C-ABI: last-error string, version, tensor-map creation.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.h"
 
@@ -25,6 +27,22 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 static std::once_flag g_encode_once;
 
+// Encoded tensor maps are cached: the engine issues the same GEMM / attention launches (same buffers, same shapes)
+// thousands of times per track, and cuTensorMapEncodeTiled costs microseconds of host time per call.
+struct TmapKey {
+    uint64_t v[11];
+    bool operator==(const TmapKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = 1469598103934665603ull;
+        for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+        return static_cast<size_t>(h);
+    }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mutex;
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
     return make_tmap(out, base, 2, rank, dims, strides_bytes, box, 1);
@@ -41,6 +59,19 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
     });
     if (g_encode == nullptr) return set_error(B200X_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(B200X_ERR_INVALID, "tensor map base not 16-byte aligned");
+    TmapKey key{};
+    key.v[0] = reinterpret_cast<uintptr_t>(base);
+    key.v[1] = static_cast<uint64_t>(elem_bytes) | (static_cast<uint64_t>(rank) << 8) | (static_cast<uint64_t>(swizzle128) << 16);
+    for (int i = 0; i < rank; ++i) {
+        key.v[2 + i] = dims[i];
+        key.v[5 + i] = box[i];
+        if (i > 0) key.v[8 + i - 1] = strides_bytes[i - 1];
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_tmap_mutex);
+        auto it = g_tmap_cache.find(key);
+        if (it != g_tmap_cache.end()) { *out = it->second; return B200X_OK; }
+    }
     cuuint64_t gdim[3];
     cuuint64_t gstr[2];
     cuuint32_t bdim[3], estr[3];
@@ -58,6 +89,11 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(B200X_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    {
+        std::lock_guard<std::mutex> lock(g_tmap_mutex);
+        if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+        g_tmap_cache.emplace(key, *out);
+    }
     return B200X_OK;
 }
 

@@ -19,6 +19,17 @@ def _ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
 
 
+def _pinned(shape, dtype) -> np.ndarray:
+    """Page-locked host array (torch's caching host allocator) so that device->host copies run at PCIe speed without a
+    driver staging copy; the numpy view keeps the allocation alive."""
+    try:
+        import torch
+
+        return torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True).numpy()
+    except Exception:                      # no torch / no CUDA runtime in this interpreter: plain pageable memory
+        return np.empty(shape, dtype)
+
+
 def _c_config(cfg: SpecTTTraConfig) -> _lib.ModelConfig:
     return _lib.ModelConfig(
         sample_rate=cfg.sample_rate, n_fft=cfg.n_fft, hop_length=cfg.hop_length, n_mels=cfg.n_mels,
@@ -135,10 +146,10 @@ class Engine:
             return []
         hop = self.cfg.hop_length
         stride = int(max(1, int((w[:, 1] - w[:, 0]).max()) * hop))
-        out = np.zeros((w.shape[0], stride), np.float32)
+        out = _pinned((w.shape[0], stride), np.float32)
         lens = np.zeros(w.shape[0], np.int64)
         _lib.check(self.lib.b200x_engine_window_audio(self._h, _ptr(w), w.shape[0], _ptr(out), stride, _ptr(lens)), "window_audio")
-        return [out[i, : int(lens[i])].copy() for i in range(w.shape[0])]
+        return [out[i, : int(lens[i])] for i in range(w.shape[0])]
 
     def occluded_audio(self, windows: np.ndarray, occlusion_value: float = 0.0) -> np.ndarray:
         w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
@@ -159,7 +170,7 @@ class Engine:
         w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
         d = np.ascontiguousarray(np.asarray(delta, dtype=np.float64))
         f, t = self.track_shape()
-        out = np.empty((f, t), np.float64)
+        out = _pinned((f, t), np.float64)
         _lib.check(self.lib.b200x_engine_saliency_map(self._h, _ptr(w), _ptr(d), w.shape[0], _ptr(out)), "saliency_map")
         return out
 
