@@ -78,6 +78,7 @@ SIGNATURES = {
     "b200x_engine_set_trace": (C.c_int, [VP, VP]),
     "b200x_engine_launch_count": (C.c_int64, [VP]),
     "b200x_engine_set_timing": (C.c_int, [VP, C.c_int]),
+    "b200x_engine_set_graphs": (C.c_int, [VP, C.c_int]),
     "b200x_engine_get_timing": (C.c_int, [VP, VP, VP]),
     "b200x_engine_stream": (VP, [VP]),
     "b200x_engine_synchronize": (C.c_int, [VP]),

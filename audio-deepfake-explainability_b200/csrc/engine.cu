@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.h"
@@ -90,6 +91,14 @@ struct b200x_engine {
     int last_copies = 0;
     float* trace = nullptr;
 
+    // CUDA graphs of the classifier forward, one per chunk shape: the ~90 launches of a chunk are replayed with one
+    // cudaGraphLaunch (inter-kernel gaps shrink, no host work per kernel).  state 0 = unseen (run eagerly once: lazy
+    // one-time initialisation must not happen inside a capture), 1 = warmed (capture on the next use), 2 = ready.
+    struct ChunkGraph { int state = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    std::map<std::tuple<int, int64_t, int, int>, ChunkGraph> graphs;
+    bool use_graphs = true;
+    DevBuf prob_chunk, logit_chunk, ranges_chunk;      // fixed addresses baked into the graphs
+
     // optional per-kernel-class CUDA-event timing (bench roofline breakdown)
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -148,8 +157,8 @@ int ensure_grow(DevBuf& b, size_t bytes) {
 }
 
 // The SpecTTTra forward over `copies` waves already sitting in e->y (rows of y_stride floats, n_samples valid).
-int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* d_sumsq, int64_t rms_count, float* d_prob,
-                  float* d_logit, const int32_t* d_ranges = nullptr, int max_range = 0) {
+int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const double* d_sumsq, int64_t rms_count, float* d_prob,
+                       float* d_logit, const int32_t* d_ranges, int max_range) {
     const b200x_model_config& c = e->cfg;
     cudaStream_t s = e->stream;
     const int n_frames = 1 + static_cast<int>(n_samples / c.hop_length);
@@ -203,6 +212,47 @@ int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* 
     TIMED(KC_HEAD, b200x_head(e->x.as<float>(), copies, T, D, e->fn_g.as<float>(), e->fn_b.as<float>(), c.block_ln_eps, c.final_norm,
                          e->cls_w.as<float>(), e->cls_b, e->head_part.as<float>(), d_logit, d_prob, s));
     e->launches += 2;
+    return B200X_OK;
+}
+
+// forward_chunk = forward_chunk_body, replayed from a CUDA graph once the chunk shape has been seen twice
+int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* d_sumsq, int64_t rms_count, float* d_prob,
+                  float* d_logit, const int32_t* d_ranges = nullptr, int max_range = 0) {
+    // the loudness-normalised FBP path bakes a per-track scalar (ref_rms) into its launches: it stays eager
+    const bool graphable = e->use_graphs && !e->timing && e->trace == nullptr && d_sumsq == nullptr;
+    if (!graphable) return forward_chunk_body(e, copies, n_samples, d_sumsq, rms_count, d_prob, d_logit, d_ranges, max_range);
+    cudaStream_t s = e->stream;
+    if (d_ranges != nullptr)
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->ranges_chunk.p, d_ranges, static_cast<size_t>(copies) * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    const int32_t* g_ranges = d_ranges ? e->ranges_chunk.as<int32_t>() : nullptr;
+    float* g_prob = e->prob_chunk.as<float>();
+    float* g_logit = e->logit_chunk.as<float>();
+    b200x_engine::ChunkGraph& g = e->graphs[std::make_tuple(copies, n_samples, d_ranges ? 1 : 0, max_range)];
+    if (g.state == 0) {
+        B200X_TRY(forward_chunk_body(e, copies, n_samples, nullptr, 0, g_prob, g_logit, g_ranges, max_range));
+        g.state = 1;
+    } else {
+        if (g.state == 1) {
+            const int64_t before = e->launches;
+            B200X_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = forward_chunk_body(e, copies, n_samples, nullptr, 0, g_prob, g_logit, g_ranges, max_range);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            g.launches = e->launches - before;
+            e->launches = before;
+            if (rc != B200X_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return set_error(B200X_ERR_CUDA, "graph capture of the forward pass failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return set_error(B200X_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+            g.state = 2;
+        }
+        B200X_CUDA_TRY(cudaGraphLaunch(g.exec, s));
+        e->launches += g.launches;
+    }
+    B200X_CUDA_TRY(cudaMemcpyAsync(d_prob, g_prob, static_cast<size_t>(copies) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (d_logit != nullptr)
+        B200X_CUDA_TRY(cudaMemcpyAsync(d_logit, g_logit, static_cast<size_t>(copies) * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return B200X_OK;
 }
 
@@ -285,6 +335,9 @@ extern "C" int b200x_engine_create(const b200x_model_config* cfg, int copies_per
     A(e->db_base, static_cast<size_t>(e->max_frames) * cfg->n_mels * sizeof(float));
     A(e->base_pre, static_cast<size_t>(e->max_frames + 1) * sizeof(float));
     A(e->base_suf, static_cast<size_t>(e->max_frames + 1) * sizeof(float));
+    A(e->prob_chunk, static_cast<size_t>(C) * sizeof(float));
+    A(e->logit_chunk, static_cast<size_t>(C) * sizeof(float));
+    A(e->ranges_chunk, static_cast<size_t>(C) * 2 * sizeof(int32_t));
     if (st != B200X_OK) { b200x_engine_destroy(e); return st; }
     cudaMemset(e->y.p, 0, e->y.bytes);
     *out = e;
@@ -293,10 +346,12 @@ extern "C" int b200x_engine_create(const b200x_model_config* cfg, int copies_per
 
 extern "C" void b200x_engine_destroy(b200x_engine* e) {
     if (!e) return;
+    for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();
     DevBuf* bufs[] = {&e->tok_t_w, &e->tok_s_w, &e->tok_t_b, &e->tok_s_b, &e->pe_t, &e->pe_s, &e->np_t_g, &e->np_t_b, &e->np_s_g,
                       &e->np_s_b, &e->fn_g, &e->fn_b, &e->cls_w, &e->wave, &e->S, &e->y, &e->db, &e->cta_max, &e->partial,
                       &e->floor_v, &e->img_t, &e->img_f, &e->x, &e->h, &e->qkv, &e->att, &e->hid, &e->head_part, &e->prob,
-                      &e->logit, &e->sumsq, &e->db_base, &e->base_pre, &e->base_suf, &e->ranges, &e->windows, &e->gains, &e->masks, &e->stems, &e->delta, &e->order, &e->map};
+                      &e->logit, &e->sumsq, &e->db_base, &e->base_pre, &e->base_suf, &e->ranges, &e->prob_chunk, &e->logit_chunk, &e->ranges_chunk, &e->windows, &e->gains, &e->masks, &e->stems, &e->delta, &e->order, &e->map};
     for (DevBuf* b : bufs) b->release();
     for (LayerW& w : e->layers) {
         DevBuf* lb[] = {&w.qkv_w, &w.qkv_b, &w.proj_w, &w.proj_b, &w.fc1_w, &w.fc1_b, &w.fc2_w, &w.fc2_b, &w.n1_g, &w.n1_b, &w.n2_g, &w.n2_b};
@@ -398,6 +453,8 @@ extern "C" int b200x_engine_finalize(b200x_engine* e) {
     B200X_TRY(get_param(e, "classifier.bias", 1, &p));
     e->cls_b = (*p)[0];
     e->params.clear();
+    for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    e->graphs.clear();                         // the weight buffers were re-allocated: captured pointers are stale
     e->finalized = true;
     return B200X_OK;
 }
@@ -761,6 +818,12 @@ extern "C" void* b200x_engine_stream(b200x_engine* e) { return e ? static_cast<v
 extern "C" int b200x_engine_synchronize(b200x_engine* e) {
     B200X_REQUIRE(e != nullptr, "synchronize: engine is NULL");
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_set_graphs(b200x_engine* e, int enable) {
+    B200X_REQUIRE(e != nullptr, "set_graphs: engine is NULL");
+    e->use_graphs = enable != 0;
     return B200X_OK;
 }
 

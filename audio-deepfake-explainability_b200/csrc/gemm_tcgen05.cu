@@ -222,7 +222,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
                             float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
                             float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
-                            if (p.act_gelu) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3); }
+                            if (p.act_gelu) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
                             w[i / 2] = pack_bf16(v0, v1);
                             w[i / 2 + 1] = pack_bf16(v2, v3);
                         }
@@ -241,7 +241,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
                             float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
                             float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
-                            if (p.act_gelu) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3); }
+                            if (p.act_gelu) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
                             w[i / 2] = pack_bf16(v0, v1);
                             w[i / 2 + 1] = pack_bf16(v2, v3);
                         }

@@ -241,4 +241,32 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return x * (x < 0.f ? h : 1.0f - h);
 }
 
+// Two exact-GELU evaluations per call with packed fp32x2 math (same polynomial as gelu_fast): the MLP epilogue is bound
+// by instruction issue, and FFMA2 / FADD2 / FMUL2 halve the slots of the Horner chain.  Phi(x) = 1/2 + sgn(x) (1/2 - h).
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+    const float z0 = fminf(fabsf(x0) * 0.70710678118654752440f, 4.2f), z1 = fminf(fabsf(x1) * 0.70710678118654752440f, 4.2f);
+    const uint64_t z = pack_f32x2(z0, z1);
+    uint64_t p = pack_f32x2(2.14887238e-05f, 2.14887238e-05f);
+    p = ffma2(p, z, pack_f32x2(-5.02961095e-04f, -5.02961095e-04f));
+    p = ffma2(p, z, pack_f32x2(5.31912975e-03f, 5.31912975e-03f));
+    p = ffma2(p, z, pack_f32x2(-3.41791940e-02f, -3.41791940e-02f));
+    p = ffma2(p, z, pack_f32x2(1.52822255e-01f, 1.52822255e-01f));
+    p = ffma2(p, z, pack_f32x2(9.16801392e-01f, 9.16801392e-01f));
+    p = ffma2(p, z, pack_f32x2(1.62814470e+00f, 1.62814470e+00f));
+    p = ffma2(p, z, pack_f32x2(-5.82025152e-06f, -5.82025152e-06f));
+    float p0, p1;
+    unpack_f32x2(p, p0, p1);
+    // t = 1/2 - h = 1/2 - 1/2 erfc(|x| / sqrt 2) in [0, 1/2];  Phi = 1/2 + copysign(t, x)
+    const uint64_t t = ffma2(pack_f32x2(ex2_approx(-p0), ex2_approx(-p1)), pack_f32x2(-0.5f, -0.5f), pack_f32x2(0.5f, 0.5f));
+    float t0, t1;
+    unpack_f32x2(t, t0, t1);
+    const uint64_t phi = fadd2(pack_f32x2(copysignf(t0, x0), copysignf(t1, x1)), pack_f32x2(0.5f, 0.5f));
+    unpack_f32x2(fmul2(pack_f32x2(x0, x1), phi), x0, x1);
+}
+
 }  // namespace b200x

@@ -199,6 +199,10 @@ class Engine:
 
     KERNEL_CLASSES = ("istft", "mel", "resize", "gemm", "attention", "layernorm", "head", "other")
 
+    def set_graphs(self, enable: bool) -> None:
+        """Replay the per-chunk classifier forward from a CUDA graph (default) or launch kernel by kernel."""
+        _lib.check(self.lib.b200x_engine_set_graphs(self._h, int(enable)), "set_graphs")
+
     def set_timing(self, enable: bool) -> None:
         _lib.check(self.lib.b200x_engine_set_timing(self._h, int(enable)), "set_timing")
 

@@ -205,6 +205,9 @@ int64_t b200x_engine_launch_count(b200x_engine* e);
 /* per-kernel-class CUDA-event timing on the engine stream: classes 0 istft, 1 mel, 2 normalise/resize, 3 gemm,
  * 4 attention, 5 layernorm, 6 head, 7 other; get_timing returns the sums since set_timing / the last get (8 entries). */
 int b200x_engine_set_timing(b200x_engine* e, int enable);
+/* The classifier forward of a chunk is replayed from a CUDA graph once its shape has been seen twice (default on);
+ * 0 = always launch kernel by kernel.  Results are identical either way. */
+int b200x_engine_set_graphs(b200x_engine* e, int enable);
 int b200x_engine_get_timing(b200x_engine* e, double* ms_per_class, int64_t* launches_per_class);
 void* b200x_engine_stream(b200x_engine* e);
 int b200x_engine_synchronize(b200x_engine* e);

@@ -145,3 +145,18 @@ def test_errors_are_loud(sd):
     bad.pop("classifier.bias")
     with pytest.raises(RuntimeError):
         Engine(CFG, bad, copies_per_chunk=2, max_samples=8 * 16000)
+
+
+def test_graph_replay_is_bit_identical_to_eager_launches(eng):
+    """The CUDA-graph replay of a chunk (third and later sweeps of a shape) must reproduce the eager launches exactly."""
+    y = synth.synth_track("SUNO", 3, 16000, 6.0)
+    eng.set_track(y)
+    n_freq, n_time = eng.track_shape()
+    wins = grid.occlusion_windows(n_freq, n_time, 64, 32, 25.0, 12.5)[:11]
+    eng.set_graphs(False)
+    eager = eng.occlusion_sweep(wins, 0.0)
+    eng.set_graphs(True)
+    runs = [eng.occlusion_sweep(wins, 0.0) for _ in range(3)]      # eager warm-up, capture + launch, replay
+    for r in runs:
+        assert np.array_equal(r, eager)
+    assert np.array_equal(eng.predict(np.stack([y, y[::-1].copy()])), np.concatenate([eng.predict(y)[None], eng.predict(y[::-1].copy())[None]]))
