@@ -1,10 +1,11 @@
 // Engine: host-side orchestration of the perturbation sweep behind the C ABI (include/b200xai.h).
 //
 // One engine per GPU / process.  Per track: wave and explainer STFT stay resident in HBM.  A sweep of N perturbed
-// copies is processed in chunks of `copies_per_chunk` so that the activation working set of the SpecTTTra forward
-// (residual stream fp32, LN output / qkv / attention / MLP hidden in bf16) stays resident in the 126 MB L2 while
-// the 12 encoder layers run over it; the perturbed spectrograms themselves are never materialised (the mask is
-// generated in the iSTFT load stage).  Everything is enqueued on one stream; no allocation in steady state.
+// copies is processed in chunks of `copies_per_chunk`; the perturbed spectrograms themselves are never materialised
+// (the mask is generated in the iSTFT load stage).  Chunks should be LARGE (>= 100 copies, ~22 MB of workspace per
+// copy at 120 s / 16 kHz): every kernel of the forward is a persistent / one-wave-per-SM launch whose prologue, tail
+// and launch gap cost microseconds, so 16-copy chunks sized for L2 residency measured 25 % slower than one 228-copy
+// chunk (tools/phase_times.py).  Everything is enqueued on one stream; no allocation in steady state.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -291,7 +292,7 @@ extern "C" int b200x_engine_create(const b200x_model_config* cfg, int copies_per
     B200X_REQUIRE(cfg->f_clip == 1, "engine: f_clip=%d unsupported (alpha variant uses 1)", cfg->f_clip);
     B200X_REQUIRE(cfg->input_spec_dim == cfg->n_mels, "engine: input_spec_dim must equal n_mels (no resize along mel axis)");
     B200X_REQUIRE((cfg->t_clip * cfg->input_spec_dim) % 8 == 0 && cfg->input_temp_dim % 8 == 0, "engine: tokenizer K not 16-byte aligned");
-    B200X_REQUIRE(copies_per_chunk >= 1 && copies_per_chunk <= 256, "engine: copies_per_chunk out of range");
+    B200X_REQUIRE(copies_per_chunk >= 1 && copies_per_chunk <= 1024, "engine: copies_per_chunk out of range");
     B200X_REQUIRE(max_samples >= 4096, "engine: max_samples too small");
     int dev = 0, major = 0;
     B200X_CUDA_TRY(cudaGetDevice(&dev));

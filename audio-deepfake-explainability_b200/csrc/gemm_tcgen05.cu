@@ -84,6 +84,99 @@ __device__ __forceinline__ void epilogue_chunk_generic(const GemmParams& p, cons
     }
 }
 
+// bf16 / residual epilogue of one 128 x BN accumulator tile for one epilogue warp (lane quarter of TMEM, every other
+// column group): TMEM -> registers -> bias (+GELU) -> swizzled slab -> one TMA tensor store (or reduce-add) per slab.
+template <int BN>
+__device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
+                                                    uint8_t* slab, uint32_t t_row, int m_warp, int n_blk, int half, int lane) {
+    const int sw = lane & 7;                             // 128B-swizzle phase of this thread's slab row
+    if (p.out_mode == B200X_GEMM_OUT_BF16) {
+        // column groups of 64 (one 128-byte bf16 row per thread); BN = 208 ends with a 16-column group
+        constexpr int NG = (BN + 63) / 64;
+#pragma unroll 1
+        for (int g = half; g < NG; g += 2) {
+            const int c = g * 64;
+            const int n0 = n_blk * BN + c;
+            const bool full = (c + 64 <= BN);
+            bulk_wait_read<0>();                         // the store that last used this slab has read it
+            __syncwarp();
+            uint8_t* dst = slab;
+            if (full) {
+                uint32_t r[64];
+                tmem_ld32(t_row + c, r);
+                tmem_ld32(t_row + c + 32, r + 32);
+                tmem_wait_ld();
+                uint32_t w[32];
+#pragma unroll
+                for (int i = 0; i < 64; i += 4) {
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                    float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
+                    float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
+                    if (p.act_gelu) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
+                    w[i / 2] = pack_bf16(v0, v1);
+                    w[i / 2 + 1] = pack_bf16(v2, v3);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) =
+                        make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            } else {
+                uint32_t r[16];
+                tmem_ld16(t_row + c, r);
+                tmem_wait_ld();
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                    float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
+                    float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
+                    if (p.act_gelu) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
+                    w[i / 2] = pack_bf16(v0, v1);
+                    w[i / 2 + 1] = pack_bf16(v2, v3);
+                }
+                *reinterpret_cast<uint4*>(dst + lane * 32) = make_uint4(w[0], w[1], w[2], w[3]);       // dense 32-byte rows
+                *reinterpret_cast<uint4*>(dst + lane * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (m_warp < p.M && n0 < p.N && elect_one()) {
+                tma_store_2d(full ? &tmC : &tmCtail, dst, n0, m_warp);   // rows >= M / cols >= N are clipped by TMA
+                bulk_commit();
+            }
+        }
+    } else if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
+        // column groups of 32 fp32 (128 bytes per thread row); x += acc + bias via TMA reduce-add
+        constexpr int NG = BN / 32;
+#pragma unroll 1
+        for (int g = half; g < NG; g += 2) {
+            const int c = g * 32;
+            const int n0 = n_blk * BN + c;
+            bulk_wait_read<0>();
+            __syncwarp();
+            uint8_t* dst = slab;
+            uint32_t r[32];
+            tmem_ld32(t_row + c, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr && n0 + 4 * j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * j));
+                const float4 v = make_float4(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y,
+                                             __uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
+                *reinterpret_cast<float4*>(dst + lane * 128 + ((j ^ sw) << 4)) = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (m_warp < p.M && n0 < p.N && elect_one()) {
+                tma_reduce_add_2d(&tmC, dst, n0, m_warp);
+                bulk_commit();
+            }
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -192,97 +285,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* slab = smem + L::EPI_OFFSET + (warp - 2) * GEMM_EPI_WARP_BYTES;
         int as = 0;
         uint32_t aphase = 0;
-        const int sw = lane & 7;                         // 128B-swizzle phase of this thread's slab row
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const int m_warp = m_blk * GEMM_BM + quarter * 32;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-            if (p.out_mode == B200X_GEMM_OUT_BF16) {
-                // column groups of 64 (one 128-byte bf16 row per thread); BN = 208 ends with a 16-column group
-                constexpr int NG = (BN + 63) / 64;
-#pragma unroll 1
-                for (int g = half; g < NG; g += 2) {
-                    const int c = g * 64;
-                    const int n0 = n_blk * BN + c;
-                    const bool full = (c + 64 <= BN);
-                    bulk_wait_read<0>();                         // the store that last used this slab has read it
-                    __syncwarp();
-                    uint8_t* dst = slab;
-                    if (full) {
-                        uint32_t r[64];
-                        tmem_ld32(t_row + c, r);
-                        tmem_ld32(t_row + c + 32, r + 32);
-                        tmem_wait_ld();
-                        uint32_t w[32];
-#pragma unroll
-                        for (int i = 0; i < 64; i += 4) {
-                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-                            float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
-                            float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
-                            if (p.act_gelu) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
-                            w[i / 2] = pack_bf16(v0, v1);
-                            w[i / 2 + 1] = pack_bf16(v2, v3);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) =
-                                make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-                    } else {
-                        uint32_t r[16];
-                        tmem_ld16(t_row + c, r);
-                        tmem_wait_ld();
-                        uint32_t w[8];
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-                            float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
-                            float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
-                            if (p.act_gelu) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
-                            w[i / 2] = pack_bf16(v0, v1);
-                            w[i / 2 + 1] = pack_bf16(v2, v3);
-                        }
-                        *reinterpret_cast<uint4*>(dst + lane * 32) = make_uint4(w[0], w[1], w[2], w[3]);       // dense 32-byte rows
-                        *reinterpret_cast<uint4*>(dst + lane * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (m_warp < p.M && n0 < p.N && elect_one()) {
-                        tma_store_2d(full ? &tmC : &tmCtail, dst, n0, m_warp);   // rows >= M / cols >= N are clipped by TMA
-                        bulk_commit();
-                    }
-                }
-            } else if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
-                // column groups of 32 fp32 (128 bytes per thread row); x += acc + bias via TMA reduce-add
-                constexpr int NG = BN / 32;
-#pragma unroll 1
-                for (int g = half; g < NG; g += 2) {
-                    const int c = g * 32;
-                    const int n0 = n_blk * BN + c;
-                    bulk_wait_read<0>();
-                    __syncwarp();
-                    uint8_t* dst = slab;
-                    uint32_t r[32];
-                    tmem_ld32(t_row + c, r);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias != nullptr && n0 + 4 * j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * j));
-                        const float4 v = make_float4(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y,
-                                                     __uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
-                        *reinterpret_cast<float4*>(dst + lane * 128 + ((j ^ sw) << 4)) = v;
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (m_warp < p.M && n0 < p.N && elect_one()) {
-                        tma_reduce_add_2d(&tmC, dst, n0, m_warp);
-                        bulk_commit();
-                    }
-                }
+            if (p.out_mode != B200X_GEMM_OUT_F32_TOKEN) {
+                epilogue_store_tile<BN>(p, tmC, tmCtail, slab, t_row, m_warp, n_blk, half, lane);
             } else {
                 // token mode: generic transposing path (row remap + positional encoding), 32-column chunks
                 float* stage = reinterpret_cast<float*>(slab);

@@ -46,7 +46,7 @@ class Engine:
     """One engine per GPU / process.  ``state_dict``: sonics-named float32 arrays (see weights.py)."""
 
     def __init__(self, cfg: SpecTTTraConfig = ALPHA_120S, state_dict: Optional[Dict[str, np.ndarray]] = None,
-                 copies_per_chunk: int = 16, max_samples: int = 120 * 16000, device: int = 0):
+                 copies_per_chunk: int = 128, max_samples: int = 120 * 16000, device: int = 0):
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = device

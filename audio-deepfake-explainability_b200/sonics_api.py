@@ -36,7 +36,7 @@ class B200Predictor:
 
     def __init__(self, model_name: str = "awsaf49/sonics-spectttra-alpha-120s", device: str = "cuda",
                  state_dict: Optional[Dict[str, np.ndarray]] = None, cfg: SpecTTTraConfig = ALPHA_120S,
-                 copies_per_chunk: int = 16, max_samples: int = 120 * 44100, device_index: Optional[int] = None):
+                 copies_per_chunk: int = 128, max_samples: int = 120 * 44100, device_index: Optional[int] = None):
         if device != "cuda":
             raise RuntimeError(f"B200Predictor runs on CUDA only (device={device!r}); it has no CPU path")
         self.model_name = model_name

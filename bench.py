@@ -154,8 +154,8 @@ def workload_config(n_gpus: int, chunk):
     return {"workload": "configs[1]: occlusion sweep, one synthetic 120 s 16 kHz track per GPU, random-init SpecTTTra-alpha-120s, "
                         "1024-frame x 5% window, half-window stride (228 evals) + baseline + saliency map + top-5 window iSTFT",
             "windows_per_track": 228, "tracks": n_gpus, "copies_per_chunk": chunk,
-            "l2_policy": "inputs larger than L2: each step streams 228 x (30.8 MB spectrogram reads + 7.7 MB waveform) and "
-                         ">100 MB of activations per chunk",
+            "l2_policy": "inputs larger than L2: every step streams the 228-copy activation set (~2.3 GB: residual stream, "
+                         "qkv, attention, MLP hidden) plus 228 x 1035 spectrogram rows through the 126 MB L2",
             "parallelism": f"windows/tracks sharded over {n_gpus} GPU(s), one NCCL all-gather of probabilities"}
 
 
@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--chunk", type=int, default=16, help="perturbed copies per pass (L2-resident working set)")
+    ap.add_argument("--chunk", type=int, default=228, help="perturbed copies per pass (one chunk = the whole 228-window sweep)")
     ap.add_argument("--cpu-evals", type=int, default=10, help="bounded CPU-baseline sample (perturbed evals)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -153,7 +153,8 @@ typedef struct b200x_model_config {
     float tokenizer_ln_eps, block_ln_eps;
 } b200x_model_config;
 
-/* copies_per_chunk: perturbed copies processed per pass (activation working set sized to stay L2-resident). */
+/* copies_per_chunk (1..1024): perturbed copies processed per pass; large chunks amortise per-launch costs (~22 MB of
+ * device workspace per copy at 120 s / 16 kHz). */
 int b200x_engine_create(const b200x_model_config* cfg, int copies_per_chunk, int64_t max_samples, b200x_engine** out);
 void b200x_engine_destroy(b200x_engine* e);
 

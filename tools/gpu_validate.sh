@@ -9,14 +9,14 @@ python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; echo "pytes
 python __graft_entry__.py --smoke > $out/smoke_$tag.log 2>&1; echo "smoke exit $?" | tee -a $out/summary_$tag.txt
 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; echo "ref exit $?" | tee -a $out/summary_$tag.txt
 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench exit $?" | tee -a $out/summary_$tag.txt
-python tools/kernel_bench.py > $out/kb_$tag.txt 2>&1; echo "kb exit $?" | tee -a $out/summary_$tag.txt
-KB_ATTN_VARIANTS=1 python tools/kernel_bench.py > $out/kbv_$tag.txt 2>&1
+python tools/kernel_bench.py 64 > $out/kb_$tag.txt 2>&1; echo "kb exit $?" | tee -a $out/summary_$tag.txt
+KB_ATTN_VARIANTS=1 python tools/kernel_bench.py 64 > $out/kbv_$tag.txt 2>&1
 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/plain_$tag.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 2500 --csv --log-file $out/launches_$tag.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 1200 --csv --log-file $out/launches_$tag.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_launches_$tag.log 2>&1
 echo "ncu launches exit $?" | tee -a $out/summary_$tag.txt
-KB_ITERS=1 KB_WARMUP=1 python tools/kernel_bench.py > $out/plain_kb_$tag.log 2>&1 &&
+KB_ITERS=1 KB_WARMUP=1 python tools/kernel_bench.py 64 > $out/plain_kb_$tag.log 2>&1 &&
 KB_ITERS=1 KB_WARMUP=1 ncu --set full --clock-control none --import-source on -k regex:'gemm_bf16|attention|layernorm|istft|mel' \
-    -o $out/prof_$tag -f python tools/kernel_bench.py > $out/ncu_full_$tag.log 2>&1
+    -o $out/prof_$tag -f python tools/kernel_bench.py 64 > $out/ncu_full_$tag.log 2>&1
 echo "ncu full exit $?" | tee -a $out/summary_$tag.txt
 tail -3 $out/pytest_gpu_$tag.log; cat $out/bench_$tag.json; cat $out/kb_$tag.txt $out/kbv_$tag.txt
