@@ -15,6 +15,7 @@
 
 #include "common.h"
 #include "fft.cuh"
+#include "ptx.cuh"
 
 namespace b200x {
 
@@ -23,7 +24,9 @@ constexpr int HOP = 512;
 constexpr int NBIN = 1025;
 constexpr int DSP_WARPS = 4;                    // warps per CTA for the FFT kernels
 constexpr int DSP_THREADS = DSP_WARPS * 32;
-constexpr int DSP_SMEM = DSP_WARPS * FFT_TILE * 8;
+constexpr int DSP_SMEM = (DSP_WARPS * FFT_TILE + FFT_TWIDDLE) * 8;
+constexpr int ISTFT_ROW = 1026;                 // float2 elements copied per spectrogram row (1025 bins + 1: 16-byte multiple)
+constexpr int ISTFT_SMEM = DSP_SMEM + DSP_WARPS * 2 * ISTFT_ROW * 8 + DSP_WARPS * 2 * 8;
 
 __global__ void init_tables_kernel() {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,9 +82,11 @@ __device__ __forceinline__ void rfft_unpack(const float2 (&v)[32], float2* tile,
 __global__ void __launch_bounds__(DSP_THREADS)
 stft_kernel(const float* __restrict__ y, long long n_samples, int n_frames, int reflect, float2* __restrict__ S,
             int stride) {
-    extern __shared__ float2 dsp_smem[];
+    extern __shared__ __align__(16) float2 dsp_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* tile = dsp_smem + warp * FFT_TILE;
+    float2* tw = dsp_smem + DSP_WARPS * FFT_TILE;
+    fft_fill_twiddles(tw);
     for (int t = blockIdx.x * DSP_WARPS + warp; t < n_frames; t += gridDim.x * DSP_WARPS) {
         const long long base = static_cast<long long>(t) * HOP - NFFT / 2;
         float2 v[32];
@@ -103,7 +108,7 @@ stft_kernel(const float* __restrict__ y, long long n_samples, int n_frames, int 
             const float2 w = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
             v[r] = make_float2(a * w.x, b * w.y);
         }
-        fft1024_warp<false>(v, tile, lane);
+        fft1024_warp<false>(v, tile, tw, lane);
         float2 X[32], xn;
         rfft_unpack(v, tile, lane, X, xn);
         float2* row = S + static_cast<long long>(t) * stride;
@@ -133,9 +138,11 @@ struct IstftParams {
 
 __global__ void __launch_bounds__(DSP_THREADS)
 istft_masked_kernel(IstftParams p) {
-    extern __shared__ float2 dsp_smem[];
+    extern __shared__ __align__(16) float2 dsp_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* tile = dsp_smem + warp * FFT_TILE;
+    float2* tw = dsp_smem + DSP_WARPS * FFT_TILE;
+    fft_fill_twiddles(tw);
     const int copy = blockIdx.y;
     const int strip = blockIdx.x * DSP_WARPS + warp;
     // padded hops [hp_a, hp_b) of this strip; valid output hops are 2 .. n_frames (restricted to what frames [ma, mb) read)
@@ -162,16 +169,39 @@ istft_masked_kernel(IstftParams p) {
     for (int i = 0; i < 8; ++i) a0[i] = a1[i] = a2[i] = make_float2(0.f, 0.f);
     float sq = 0.f;
 
-    for (int t = max(hp_a - 3, 0); t < hp_b; ++t) {
+    // spectrogram rows are staged through shared memory with 1-D TMA bulk copies, double-buffered per warp: the copy of
+    // frame t + 1 is in flight while frame t is transformed (the load stage used to stall on L2 latency, 61 % of samples)
+    float2* rowbuf = dsp_smem + DSP_WARPS * FFT_TILE + FFT_TWIDDLE + warp * 2 * ISTFT_ROW;
+    uint64_t* rbar = reinterpret_cast<uint64_t*>(dsp_smem + DSP_WARPS * FFT_TILE + FFT_TWIDDLE + DSP_WARPS * 2 * ISTFT_ROW) + warp * 2;
+    const int t_first = max(hp_a - 3, 0);
+    if (lane == 0) {
+        mbar_init(&rbar[0], 1);
+        mbar_init(&rbar[1], 1);
+        fence_barrier_init();
+        if (t_first < p.n_frames) {
+            mbar_expect_tx(&rbar[0], ISTFT_ROW * 8);
+            bulk_load_1d(rowbuf, p.S + static_cast<long long>(t_first) * p.stride, ISTFT_ROW * 8, &rbar[0]);
+        }
+    }
+    __syncwarp();
+
+    for (int t = t_first; t < hp_b; ++t) {
         float2 v[32];
+        const int it = t - t_first;
+        if (lane == 0 && t + 1 < hp_b && t + 1 < p.n_frames) {      // the other buffer was read in the previous iteration
+            uint64_t* nb = &rbar[(it + 1) & 1];
+            mbar_expect_tx(nb, ISTFT_ROW * 8);
+            bulk_load_1d(rowbuf + ((it + 1) & 1) * ISTFT_ROW, p.S + static_cast<long long>(t + 1) * p.stride, ISTFT_ROW * 8, nb);
+        }
         if (t < p.n_frames) {
-            const float2* row = p.S + static_cast<long long>(t) * p.stride;
+            mbar_wait(&rbar[it & 1], (it >> 1) & 1);
+            const float2* row = rowbuf + (it & 1) * ISTFT_ROW;
             const bool t_in = (t >= t0 && t < t1);
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const int k = lane + 32 * r, kp = 1024 - k;
-                float2 xk = __ldg(&row[k]);
-                float2 xp = __ldg(&row[kp]);
+                float2 xk = row[k];
+                float2 xp = row[kp];
                 if (p.mode == 1) {
                     if (t_in && k >= f0 && k < f1) xk = make_float2(p.occlusion_value, 0.f);
                     if (t_in && kp >= f0 && kp < f1) xp = make_float2(p.occlusion_value, 0.f);
@@ -190,7 +220,7 @@ istft_masked_kernel(IstftParams p) {
                 const float orr = dr * w.x - di * w.y, oi = dr * w.y + di * w.x;
                 v[r] = make_float2(er - oi, ei + orr);
             }
-            fft1024_warp<true>(v, tile, lane);
+            fft1024_warp<true>(v, tile, tw, lane);
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const float2 w = *reinterpret_cast<const float2*>(&g_hann[2 * (lane + 32 * r)]);
@@ -235,6 +265,7 @@ istft_masked_kernel(IstftParams p) {
             a1[i] = make_float2(a2[i].x + v[16 + i].x, a2[i].y + v[16 + i].y);
             a2[i] = v[24 + i];
         }
+        __syncwarp();
     }
     if (p.sumsq != nullptr) {
         double d = static_cast<double>(sq);
@@ -268,10 +299,12 @@ struct MelParams {
 
 __global__ void __launch_bounds__(DSP_THREADS)
 mel_db_kernel(MelParams p) {
-    extern __shared__ float2 dsp_smem[];
+    extern __shared__ __align__(16) float2 dsp_smem[];
     __shared__ float s_max[DSP_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* tile = dsp_smem + warp * FFT_TILE;
+    float2* tw = dsp_smem + DSP_WARPS * FFT_TILE;
+    fft_fill_twiddles(tw);
     float* pw = reinterpret_cast<float*>(tile);
     const int copy = blockIdx.y;
     const float* y = p.y + static_cast<long long>(copy) * p.y_stride;
@@ -306,7 +339,7 @@ mel_db_kernel(MelParams p) {
             const float2 w = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
             v[r] = make_float2(s.x * gain * w.x, s.y * gain * w.y);
         }
-        fft1024_warp<false>(v, tile, lane);
+        fft1024_warp<false>(v, tile, tw, lane);
         float2 X[32], xn;
         rfft_unpack(v, tile, lane, X, xn);
 #pragma unroll
@@ -489,10 +522,13 @@ __global__ void frame_ranges_kernel(const int* __restrict__ windows, int n, int 
 __global__ void base_maxima_kernel(const float* __restrict__ db, int n_frames, int n_mels, float* __restrict__ pre,
                                    float* __restrict__ suf) {
     extern __shared__ float s_fm[];                 // per-frame maxima
-    for (int t = threadIdx.x; t < n_frames; t += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int t = warp; t < n_frames; t += n_warps) {      // one warp per frame: coalesced row reads, shuffle reduction
         float m = -INFINITY;
-        for (int f = 0; f < n_mels; ++f) m = fmaxf(m, db[static_cast<long long>(t) * n_mels + f]);
-        s_fm[t] = m;
+        for (int f = lane; f < n_mels; f += 32) m = fmaxf(m, db[static_cast<long long>(t) * n_mels + f]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) s_fm[t] = m;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -544,10 +580,12 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
     B200X_REQUIRE((mode != 1 && mode != 3) || d_windows != nullptr, "istft: windows missing");
     B200X_REQUIRE(mode != 2 || d_gains != nullptr, "istft: gains missing");
     B200X_REQUIRE(n_frames >= 2 && copies > 0, "istft: bad sizes");
+    B200X_REQUIRE(spec_stride >= ISTFT_ROW && spec_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(d_spec) & 15) == 0,
+                  "istft: spectrogram rows must be 16-byte aligned with stride >= %d complex values (got %d)", ISTFT_ROW, spec_stride);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     B200X_TRY(ensure_tables(s));
     static bool cfg = false;
-    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DSP_SMEM)); cfg = true; }
+    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM)); cfg = true; }
     IstftParams p;
     p.S = reinterpret_cast<const float2*>(d_spec); p.stride = spec_stride; p.n_frames = n_frames;
     p.out_len = static_cast<long long>(HOP) * (n_frames - 1); p.out_stride = y_stride; p.y = d_y;
@@ -561,7 +599,7 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
     p.hops_per_strip = (static_cast<long long>(copies) * hops >= 30000) ? 29 : 13;
     const int strips = ceil_div(hops, p.hops_per_strip);
     dim3 grid(ceil_div(strips, DSP_WARPS), copies);
-    istft_masked_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(p);
+    istft_masked_kernel<<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }
@@ -683,7 +721,7 @@ extern "C" int b200x_frame_ranges(const int32_t* d_windows, int n, int n_frames,
 extern "C" int b200x_mel_base_maxima(const float* d_db_base, int n_frames, int n_mels, float* d_premax, float* d_sufmax,
                                      void* stream) {
     B200X_REQUIRE(n_frames > 0 && n_frames <= 12000, "base_maxima: n_frames=%d out of range", n_frames);
-    base_maxima_kernel<<<1, 256, n_frames * sizeof(float), static_cast<cudaStream_t>(stream)>>>(d_db_base, n_frames, n_mels, d_premax, d_sufmax);
+    base_maxima_kernel<<<1, 1024, n_frames * sizeof(float), static_cast<cudaStream_t>(stream)>>>(d_db_base, n_frames, n_mels, d_premax, d_sufmax);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }

@@ -75,12 +75,25 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = t[i];
 }
 
+constexpr int FFT_TWIDDLE = 32 * 32;   // float2 elements of the CTA-wide inter-stage twiddle table
+
+// tw[k2 * 32 + lane] = (cos, sin)(2 pi lane k2 / 1024): the inter-stage twiddles depend only on (lane, k2), so one
+// 8 KB shared-memory table per CTA serves every frame with conflict-free 8-byte loads.  (Gathering them from the global
+// table costs up to 32 L1 wavefronts per load - lanes stride 16 k2 bytes - and was the top stall of the FFT kernels.)
+__device__ __forceinline__ void fft_fill_twiddles(float2* tw) {
+    for (int i = threadIdx.x; i < FFT_TWIDDLE; i += blockDim.x) {
+        const int k2 = i >> 5, n1 = i & 31;
+        tw[i] = g_tw2048[(2 * n1 * k2) & 2047];
+    }
+    __syncthreads();
+}
+
 template <bool INV>
-__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* tile, int lane) {
+__device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* tile, const float2* tw, int lane) {
     fft32<INV>(v);                                     // over n2 (lane = n1): v[k2]
 #pragma unroll
     for (int k2 = 1; k2 < 32; ++k2) {                  // times W_1024^(n1 k2)
-        const float2 w = __ldg(&g_tw2048[2 * lane * k2]);
+        const float2 w = tw[k2 * 32 + lane];
         const float wi = INV ? w.y : -w.y;
         const float2 x = v[k2];
         v[k2] = make_float2(x.x * w.x - x.y * wi, x.x * wi + x.y * w.x);

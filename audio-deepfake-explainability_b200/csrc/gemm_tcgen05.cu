@@ -1,6 +1,6 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] . W[N,K]^T  (+ fused epilogue)
 //
-//   warp 0    : TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring; 3 stages for BN = 256)
+//   warp 0    : TMA producer (cp.async.bulk.tensor, 128B swizzle, 3-stage mbarrier ring)
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32 accumulate in TMEM)
 //   warps 2-9 : epilogue.  TMEM lane == tile row, so tcgen05.ld hands every thread one row of the accumulator.
 //               bf16 / residual outputs: bias (+GELU) in registers, pack, st.shared into a 128B-swizzled per-warp slab
@@ -9,11 +9,13 @@
 //               token-mode outputs (tokenizer: row remap + positional encoding) take a generic coalescing path.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.  With K = 384 the epilogue is as
 // long as the MMAs, hence eight epilogue warps (two per TMEM lane quarter, splitting the column groups).
-// Pipeline depth matters more than anything else here: a ring slot cycles through "MMAs retire -> commit -> producer
-// wakes -> TMA load (L2 hit) -> issuer wakes" in ~2400 cycles while its four MMAs take ~500, so with three stages the
-// issuer waited for loads 40 % of the time (measured with the in-kernel counters, tools/gemm_profile.py).  The epilogue
-// slabs are therefore single-buffered (each warp stores at most two slabs per tile) to make room for a fourth stage.
+// What bounds it (in-kernel cycle counters, tools/gemm_profile.py): a 128 x BN tile pulls (16 KB + BN x 128 B) per 64-deep
+// k-block through the SM's L2 port, which delivers ~54 B/clk; for BN = 192 that is 40 KB per 424 MMA cycles, so the port -
+// not the tensor pipe, not the ring depth (3 vs 4 stages measured equal) - paces the kernel at ~50 % of the MMA rate.
+// Hence the CTA-pair kernel below (cta_group::2: half of the B tile per SM) for everything but the tokenizer epilogue.
 // Used for every dense contraction of the SpecTTTra forward (tokenizer projections, QKV, attention projection, MLP).
+#include <algorithm>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -21,11 +23,11 @@ namespace b200x {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;      // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_MAX_STAGES = 4;
+constexpr int GEMM_MAX_STAGES = 3;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_SLAB_BYTES = 32 * 128;             // 32 rows x 128 bytes
-constexpr int GEMM_EPI_WARP_BYTES = 5 * 1024;         // one 1024-byte-aligned slab (swizzle atom); the token path stages 32 x 36 floats
+constexpr int GEMM_EPI_WARP_BYTES = 2 * GEMM_SLAB_BYTES + 1024;   // double-buffered slab (+ spare for the token path), 1024-aligned
 
 struct GemmParams {
     int M, N, K;
@@ -84,12 +86,30 @@ __device__ __forceinline__ void epilogue_chunk_generic(const GemmParams& p, cons
     }
 }
 
+// acc (+bias) (-> GELU) -> packed bf16 for N consecutive accumulator columns; GELU is a template parameter so that the
+// plain path does not carry the (if-converted, predicated-off) GELU instructions through its issue slots
+template <int N, bool GELU>
+__device__ __forceinline__ void convert_columns(const uint32_t* r, uint32_t* w, const float* bias, int n0, int n_limit) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias != nullptr && n0 + i < n_limit) b = __ldg(reinterpret_cast<const float4*>(bias + n0 + i));
+        float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
+        float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
+        if (GELU) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
+        w[i / 2] = pack_bf16(v0, v1);
+        w[i / 2 + 1] = pack_bf16(v2, v3);
+    }
+}
+
 // bf16 / residual epilogue of one 128 x BN accumulator tile for one epilogue warp (lane quarter of TMEM, every other
 // column group): TMEM -> registers -> bias (+GELU) -> swizzled slab -> one TMA tensor store (or reduce-add) per slab.
 template <int BN>
 __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
-                                                    uint8_t* slab, uint32_t t_row, int m_warp, int n_blk, int half, int lane) {
+                                                    uint8_t* slab, int& buf, uint32_t t_row, int m_warp, int n_blk, int half, int lane,
+                                                    long long* pc = nullptr) {
     const int sw = lane & 7;                             // 128B-swizzle phase of this thread's slab row
+    long long pt = 0;
     if (p.out_mode == B200X_GEMM_OUT_BF16) {
         // column groups of 64 (one 128-byte bf16 row per thread); BN = 208 ends with a 16-column group
         constexpr int NG = (BN + 63) / 64;
@@ -98,25 +118,24 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const C
             const int c = g * 64;
             const int n0 = n_blk * BN + c;
             const bool full = (c + 64 <= BN);
-            bulk_wait_read<0>();                         // the store that last used this slab has read it
+            // nothing to store: skip the slab write too - a buffer may only be refilled behind a COMMITTED store, otherwise
+            // bulk_wait_read<1> no longer proves that the store which last used it has been read
+            if (m_warp >= p.M || n0 >= p.N) continue;
+            if (pc) pt = clock64();
+            bulk_wait_read<1>();                         // the store that last used this buffer has read it
             __syncwarp();
-            uint8_t* dst = slab;
+            if (pc) { const long long t = clock64(); pc[0] += t - pt; pt = t; }
+            uint8_t* dst = slab + buf * GEMM_SLAB_BYTES;
+            buf ^= 1;
             if (full) {
                 uint32_t r[64];
                 tmem_ld32(t_row + c, r);
                 tmem_ld32(t_row + c + 32, r + 32);
                 tmem_wait_ld();
+                if (pc) { const long long t = clock64(); pc[1] += t - pt; pt = t; }
                 uint32_t w[32];
-#pragma unroll
-                for (int i = 0; i < 64; i += 4) {
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-                    float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
-                    float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
-                    if (p.act_gelu) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
-                    w[i / 2] = pack_bf16(v0, v1);
-                    w[i / 2 + 1] = pack_bf16(v2, v3);
-                }
+                if (p.act_gelu) convert_columns<64, true>(r, w, p.bias, n0, p.N);
+                else convert_columns<64, false>(r, w, p.bias, n0, p.N);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) =
@@ -126,25 +145,19 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const C
                 tmem_ld16(t_row + c, r);
                 tmem_wait_ld();
                 uint32_t w[8];
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.bias != nullptr && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-                    float v0 = __uint_as_float(r[i]) + b.x, v1 = __uint_as_float(r[i + 1]) + b.y;
-                    float v2 = __uint_as_float(r[i + 2]) + b.z, v3 = __uint_as_float(r[i + 3]) + b.w;
-                    if (p.act_gelu) { gelu_fast2(v0, v1); gelu_fast2(v2, v3); }
-                    w[i / 2] = pack_bf16(v0, v1);
-                    w[i / 2 + 1] = pack_bf16(v2, v3);
-                }
+                if (p.act_gelu) convert_columns<16, true>(r, w, p.bias, n0, p.N);
+                else convert_columns<16, false>(r, w, p.bias, n0, p.N);
                 *reinterpret_cast<uint4*>(dst + lane * 32) = make_uint4(w[0], w[1], w[2], w[3]);       // dense 32-byte rows
                 *reinterpret_cast<uint4*>(dst + lane * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
             }
+            if (pc) { const long long t = clock64(); pc[2] += t - pt; pt = t; }
             fence_proxy_async();
             __syncwarp();
-            if (m_warp < p.M && n0 < p.N && elect_one()) {
+            if (elect_one()) {
                 tma_store_2d(full ? &tmC : &tmCtail, dst, n0, m_warp);   // rows >= M / cols >= N are clipped by TMA
                 bulk_commit();
             }
+            if (pc) { const long long t = clock64(); pc[3] += t - pt; pt = t; }
         }
     } else if (p.out_mode == B200X_GEMM_OUT_F32_RESID) {
         // column groups of 32 fp32 (128 bytes per thread row); x += acc + bias via TMA reduce-add
@@ -153,9 +166,11 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const C
         for (int g = half; g < NG; g += 2) {
             const int c = g * 32;
             const int n0 = n_blk * BN + c;
-            bulk_wait_read<0>();
+            if (m_warp >= p.M || n0 >= p.N) continue;    // see above
+            bulk_wait_read<1>();
             __syncwarp();
-            uint8_t* dst = slab;
+            uint8_t* dst = slab + buf * GEMM_SLAB_BYTES;
+            buf ^= 1;
             uint32_t r[32];
             tmem_ld32(t_row + c, r);
             tmem_wait_ld();
@@ -169,7 +184,7 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const C
             }
             fence_proxy_async();
             __syncwarp();
-            if (m_warp < p.M && n0 < p.N && elect_one()) {
+            if (elect_one()) {
                 tma_reduce_add_2d(&tmC, dst, n0, m_warp);
                 bulk_commit();
             }
@@ -283,16 +298,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter + 32)
         const int half = (warp - 2) >> 2;                // which of the two warps sharing this lane quarter
         uint8_t* slab = smem + L::EPI_OFFSET + (warp - 2) * GEMM_EPI_WARP_BYTES;
-        int as = 0;
+        int as = 0, buf = 0, tile_parity = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_parity) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
             const int m_warp = m_blk * GEMM_BM + quarter * 32;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
             if (p.out_mode != B200X_GEMM_OUT_F32_TOKEN) {
-                epilogue_store_tile<BN>(p, tmC, tmCtail, slab, t_row, m_warp, n_blk, half, lane);
+                epilogue_store_tile<BN>(p, tmC, tmCtail, slab, buf, t_row, m_warp, n_blk, half ^ (tile_parity & 1), lane);
             } else {
                 // token mode: generic transposing path (row remap + positional encoding), 32-column chunks
                 float* stage = reinterpret_cast<float*>(slab);
@@ -340,6 +355,167 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair GEMM
+// Two CTAs of a cluster (one TPC) share one 256 x BN tile through tcgen05 cta_group::2: each CTA loads its own 128 rows
+// of A and HALF of the B tile (BN/2 weight rows) and the pair's tensor cores exchange the halves.  A single-CTA
+// 128 x 192 tile has to pull 40 KB through the SM's L2 port (~54 B/clk measured) per 64-deep k-block of 424 MMA
+// cycles - the port, not the tensor pipe, bounds it (tools/gemm_profile.py).  The pair halves the B bytes per SM.
+//   warp 0 (both CTAs): TMA producer for its own shared memory; completion bytes go to the LEADER's full barrier
+//   warp 1 (leader)   : issues tcgen05.mma.cta_group::2; commits are multicast to both CTAs' empty / tfull barriers
+//   warps 2-9 (both)  : epilogue of the CTA's own 128 accumulator rows; "accumulator drained" arrives on the leader
+template <int BN>
+struct Gemm2Smem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (5 * STAGE_BYTES + GEMM_EPI_WARPS * GEMM_EPI_WARP_BYTES + 1280 <= 232448) ? 5 : 4;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + GEMM_EPI_WARPS * GEMM_EPI_WARP_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static_assert(B_BYTES % 1024 == 0, "B half tile must keep 1024-byte alignment for the 128B swizzle");
+    static_assert(TOTAL <= 232448, "shared memory budget exceeded");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCtail, GemmParams p) {
+    using L = Gemm2Smem<BN>;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    constexpr int STAGES = L::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);      // the epilogue warps of BOTH CTAs (leader's copy is used)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();                                  // barrier inits and the TMEM allocation are visible pair-wide
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                    const uint32_t leader_full = mapa_shared(&full_bar[stage], 0);
+                    tma_load_2d_pair(sa, &tmA, leader_full, kb * GEMM_BK, m_blk * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM);
+                    tma_load_2d_pair(sa + L::A_BYTES, &tmB, leader_full, kb * GEMM_BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            long long pc_full = 0, pc_te = 0, pc_t = 0, pc_tiles = 0;
+            const long long pc_start = p.prof ? clock64() : 0;
+            for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+                if (p.prof) pc_t = clock64();
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                if (p.prof) { pc_te += clock64() - pc_t; ++pc_tiles; }
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (p.prof) pc_t = clock64();
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (p.prof) pc_full += clock64() - pc_t;
+                    const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        umma_ss_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tfull_bar[as]);         // accumulator ready for both CTAs' epilogues
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (p.prof) {
+                long long* o = p.prof + blockIdx.x * 8;
+                o[0] = pc_full; o[1] = pc_te; o[2] = clock64() - pc_start; o[3] = pc_tiles;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        uint8_t* slab = smem + L::EPI_OFFSET + (warp - 2) * GEMM_EPI_WARP_BYTES;
+        int as = 0, buf = 0, tile_parity = 0;
+        uint32_t aphase = 0;
+        const uint32_t leader_tempty0 = mapa_shared(&tempty_bar[0], 0), leader_tempty1 = mapa_shared(&tempty_bar[1], 0);
+        long long pce[4] = {0, 0, 0, 0}, pc_wt = 0, pc_t0 = 0;
+        long long* pc = (p.prof != nullptr && warp == 2 && rank == 0) ? pce : nullptr;
+        for (int tile = pair; tile < num_tiles; tile += n_pairs, ++tile_parity) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            if (pc) pc_t0 = clock64();
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            if (pc) pc_wt += clock64() - pc_t0;
+            const int m_warp = m_blk * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+            epilogue_store_tile<BN>(p, tmC, tmCtail, slab, buf, t_row, m_warp, n_blk, half ^ (tile_parity & 1), lane, pc);
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive_cluster(as == 0 ? leader_tempty0 : leader_tempty1);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+        if (pc != nullptr && lane == 0) {
+            long long* o = p.prof + blockIdx.x * 8 + 6;
+            o[0] = (pce[0] << 32) | (pce[1] & 0xffffffffll);
+            o[1] = (pce[2] << 32) | (pce[3] & 0xffffffffll);
+            p.prof[(blockIdx.x + 1) * 8 + 6] = pc_wt;
+        }
+        bulk_wait<0>();                                  // all tensor stores of this warp have completed
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                  // no CTA of the pair may free TMEM / exit while the other still uses it
+    if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+}
+
 static int g_num_sms = 0;
 
 template <int BN>
@@ -363,14 +539,38 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     return B200X_OK;
 }
 
+template <int BN>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
+                        const GemmParams& p, cudaStream_t stream) {
+    using L = Gemm2Smem<BN>;
+    static bool configured = false;
+    if (!configured) {
+        B200X_CUDA_TRY(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        B200X_CUDA_TRY(cudaGetDevice(&dev));
+        B200X_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles = ceil_div(p.M, 2 * GEMM_BM) * ceil_div(p.N, BN);
+    const int pairs = std::min(tiles, g_num_sms / 2);
+    gemm2_bf16_tn_kernel<BN><<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmCtail, p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
 }  // namespace b200x
 
 using namespace b200x;
 
+static int g_gemm_pair = 1;
+// diagnostic only: 0 forces the single-CTA kernel for every problem
+extern "C" void b200x_debug_gemm_pair(int on) { g_gemm_pair = on; }
+
 static long long* g_gemm_prof = nullptr;
 // diagnostic only (not part of the public header): device buffer of 4 long long per CTA for the issuer's cycle counters
 extern "C" void b200x_debug_gemm_profile(void* d_buf) { g_gemm_prof = static_cast<long long*>(d_buf); }
-extern "C" void b200x_debug_gemm_bres(int) {}
 
 extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n,
                                void* d_out, int ldc, int out_mode, const float* d_bias, int act_gelu,
@@ -393,7 +593,9 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
     B200X_TRY(make_tmap_bf16(&tmA, d_a, 2, da, sa, ba));
     const uint64_t dw[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t sw[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t bw[2] = {GEMM_BK, static_cast<uint32_t>(block_n)};
+    // CTA-pair kernel (256 x BN tiles, each CTA loads half of the B tile) for everything but the token epilogue
+    const bool pair = g_gemm_pair && out_mode != B200X_GEMM_OUT_F32_TOKEN && block_n != 128 && M > GEMM_BM;
+    const uint32_t bw[2] = {GEMM_BK, static_cast<uint32_t>(pair ? block_n / 2 : block_n)};
     B200X_TRY(make_tmap_bf16(&tmB, d_w, 2, dw, sw, bw));
     // output maps: 32-row slabs, 128 bytes wide (64 bf16 / 32 fp32), plus a dense 16-column bf16 tail map
     const uint64_t dc[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
@@ -413,6 +615,14 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
     }
     GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off, g_gemm_prof};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (pair) {
+        switch (block_n) {
+            case 192: return launch_gemm2<192>(tmA, tmB, tmC, tmCtail, p, s);
+            case 208: return launch_gemm2<208>(tmA, tmB, tmC, tmCtail, p, s);
+            case 256: return launch_gemm2<256>(tmA, tmB, tmC, tmCtail, p, s);
+            default: break;
+        }
+    }
     switch (block_n) {
         case 128: return launch_gemm<128>(tmA, tmB, tmC, tmCtail, p, s);
         case 192: return launch_gemm<192>(tmA, tmB, tmC, tmCtail, p, s);

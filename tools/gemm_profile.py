@@ -38,5 +38,11 @@ for bres in (0,):
             p = prof.cpu().double()
             p = p[p[:, 3] > 0]
             span = (p[:, 5].max() - p[:, 4].min()) / 1e3
+            e = prof.cpu()
+            e0, e1, ew = e[0::2, 6].double(), e[0::2, 7].double(), e[1::2, 6].double()
+            nz = e0 != 0
+            if nz.any():
+                rd, ld, cp, st = (e[0::2, 6][nz] >> 32).double().mean(), (e[0::2, 6][nz] & 0xffffffff).double().mean(), (e[0::2, 7][nz] >> 32).double().mean(), (e[0::2, 7][nz] & 0xffffffff).double().mean()
+                print(f"   epilogue warp 2 per CTA: wait tfull {ew[nz].mean():8.0f}  wait slab read {rd:8.0f}  tmem ld {ld:8.0f}  compute+st.shared {cp:8.0f}  fence+tma {st:8.0f}")
             print(f"{name} bn={bn}: {us:6.1f} us/launch (events, 20 launches), in-kernel span {span:6.1f} us | issuer per CTA: total {p[:, 2].mean():8.0f} clk (max {p[:, 2].max():8.0f}), wait loads {p[:, 0].mean():8.0f}, "
                   f"wait epilogue {p[:, 1].mean():8.0f}, tiles {p[:, 3].mean():4.1f} (max {p[:, 3].max():.0f}) -> {p[:, 2].mean() / p[:, 3].mean():6.0f} clk/tile; SM clock ~{p[:, 2].max() / max(span, 1e-3) / 1e3:5.2f} GHz x span")
