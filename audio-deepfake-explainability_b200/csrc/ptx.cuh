@@ -279,6 +279,26 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// 2^x for two values on the FMA / ALU pipes only (no MUFU): Cody-Waite split x = n + f, |f| <= 1/2, a degree-3 near-minimax
+// polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of the softmax weights it feeds) and the
+// exponent inserted with an integer add.  x <= -126 returns 2^-126 (~0).  Used for a FRACTION of the attention
+// exponentials: the MUFU (16 ex2 / clk / SM) is what bounds that kernel, the FMA pipe has slots to spare.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+    const float magic = 12582912.0f;                     // 1.5 * 2^23: adding it rounds to the nearest integer in the low bits
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+    const uint64_t x = pack_f32x2(x0, x1);
+    const uint64_t t = fadd2(x, pack_f32x2(magic, magic));
+    const uint64_t f = fadd2(x, ffma2(t, pack_f32x2(-1.0f, -1.0f), pack_f32x2(magic, magic)));     // x - (t - magic)
+    uint64_t q = ffma2(f, pack_f32x2(0.0551716685f, 0.0551716685f), pack_f32x2(0.2426111251f, 0.2426111251f));
+    q = ffma2(q, f, pack_f32x2(0.6932609677f, 0.6932609677f));
+    q = ffma2(q, f, pack_f32x2(0.9999280572f, 0.9999280572f));
+    float t0, t1, q0, q1;
+    unpack_f32x2(t, t0, t1);
+    unpack_f32x2(q, q0, q1);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

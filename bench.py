@@ -174,6 +174,8 @@ def run_engine(args):
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"              # keep stdout to the one JSON line the driver parses
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = read_peaks()
 

@@ -12,7 +12,9 @@ __device__ __forceinline__ void chunk(const uint32_t* r, uint32_t* pk, uint64_t 
     for (int i = 0; i < 8; ++i) {
         float x0, x1;
         unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, link_a), x0, x1);
-        const float p0 = (MODE & 2) ? x0 : ex2_approx(x0), p1 = (MODE & 2) ? x1 : ex2_approx(x1);
+        float p0, p1;
+        if (((MODE & 8) && (i & 3) == 3) || ((MODE & 16) && (i & 1))) exp2_poly2(x0, x1, p0, p1);
+        else { p0 = (MODE & 2) ? x0 : ex2_approx(x0); p1 = (MODE & 2) ? x1 : ex2_approx(x1); }
         acc_a = fadd2(acc_a, pack_f32x2(p0, p1));
         pk[i] = pack_bf16(p0, p1);
     }
@@ -21,7 +23,9 @@ __device__ __forceinline__ void chunk(const uint32_t* r, uint32_t* pk, uint64_t 
     for (int i = 8; i < 16; ++i) {
         float x0, x1;
         unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, link_b), x0, x1);
-        const float p0 = (MODE & 2) ? x0 : ex2_approx(x0), p1 = (MODE & 2) ? x1 : ex2_approx(x1);
+        float p0, p1;
+        if (((MODE & 8) && (i & 3) == 3) || ((MODE & 16) && (i & 1))) exp2_poly2(x0, x1, p0, p1);
+        else { p0 = (MODE & 2) ? x0 : ex2_approx(x0); p1 = (MODE & 2) ? x1 : ex2_approx(x1); }
         acc_b = fadd2(acc_b, pack_f32x2(p0, p1));
         pk[i] = pack_bf16(p0, p1);
     }
@@ -86,6 +90,11 @@ int main() {
     run<0>("max + exp (MUFU), no links", 256);
     run<1>("max + exp (MUFU), linked halves", 128);
     run<1>("max + exp (MUFU), linked halves", 256);
+    run<8>("max + exp, 25% polynomial", 128);
+    run<8>("max + exp, 25% polynomial", 256);
+    run<9>("max + exp, 25% polynomial, linked", 256);
+    run<16>("max + exp, 50% polynomial", 128);
+    run<16>("max + exp, 50% polynomial", 256);
     run<2>("max + no MUFU", 128);
     run<2>("max + no MUFU", 256);
     run<4>("exp only (no max pass)", 128);
