@@ -19,21 +19,24 @@
 
 namespace b200x {
 
-constexpr int ATT_THREADS = 352;       // warps 0-3 softmax(A), 4-7 softmax(B), 8 TMA, 9 MMA(A), 10 MMA(B)
+// NQ = query tiles per CTA.  NQ = 2: one CTA per SM, two tiles ping-pong and share K / V.  NQ = 1: two CTAs per SM (half the
+// shared memory, TMEM columns and registers each); the co-resident CTAs run free of each other, so one CTA's load / max /
+// barrier phases and its prologue / epilogue fall into the other's exponential phase instead of lining up with it.
+// warps [0, 4 NQ): softmax (4 per tile), warp 4 NQ: TMA, warps 4 NQ + 1 ...: one MMA issuer per tile.
 // The producer / issuer roles sit on the HIGHEST warp ids: the SM's warp arbiter prefers higher ids, and an issuer that
 // loses its issue slots to the softmax warps delays every tcgen05.mma by hundreds of cycles.
-constexpr int ATT_W_TMA = 8, ATT_W_MMA = 9;
 constexpr int ATT_TILE = 128;
 constexpr int ATT_HD = 64;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_HD * 2;     // 16 KB
-constexpr int ATT_KV_STAGES = 4;
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 + 2 * ATT_KV_STAGES) + 256 + 1024;
-constexpr uint32_t ATT_TMEM_COLS = 512;
-constexpr uint32_t ATT_S_COL = 0, ATT_O_COL = 256, ATT_P_COL = 384;
+template <int NQ> struct AttCfg {
+    static constexpr int THREADS = 32 * (5 * NQ + 1);
+    static constexpr int W_TMA = 4 * NQ, W_MMA = 4 * NQ + 1;
+    static constexpr int KV_STAGES = NQ == 2 ? 4 : 3;
+    static constexpr int SMEM = ATT_TILE_BYTES * (NQ + 2 * KV_STAGES) + 256;     // dynamic shared memory is 1024-byte aligned
+    static constexpr uint32_t TMEM_COLS = 256 * NQ;
+    static constexpr uint32_t S_COL = 0, O_COL = 128 * NQ, P_COL = 192 * NQ;
+};
 constexpr float ATT_RESCALE_LOG2 = 8.0f;
-#ifndef ATT_ALTERNATE
-#define ATT_ALTERNATE 0
-#endif
 
 struct AttnParams {
     int tokens;        // tokens per copy (multiple of 16)
@@ -50,6 +53,12 @@ struct AttnParams {
 // which blocks the (in-order) warp on the MUFU queue while its other work waits.  The two 16-score halves of a chunk
 // therefore take their addend from `link` = fma(sum two halves back, 0, -m*c): a true data dependence on older results
 // (value unchanged) that keeps at most two halves in flight, so MUFU runs stay short and interleave with FMA work.
+// which of the 8 score pairs of a half chunk take the FMA-pipe polynomial instead of the MUFU (bit 256: 2 of 8, 8192: 1 of 8,
+// 16384: 3 of 8)
+template <int DBG>
+__device__ __forceinline__ constexpr bool att_poly_pair(int i) {
+    return ((DBG & 256) && (i & 3) == 3) || ((DBG & 8192) && (i & 7) == 7) || ((DBG & 16384) && ((i & 7) == 2 || (i & 7) == 5 || (i & 7) == 7));
+}
 template <int DBG>
 __device__ __forceinline__ void exp_chunk(const uint32_t* r, uint32_t (&pk)[16], uint64_t c2, uint64_t nmc2, uint64_t zero2,
                                           uint64_t& acc_a, uint64_t& acc_b) {
@@ -58,7 +67,9 @@ __device__ __forceinline__ void exp_chunk(const uint32_t* r, uint32_t (&pk)[16],
     for (int i = 0; i < 8; ++i) {
         float x0, x1;
         unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, link_a), x0, x1);
-        const float p0 = (DBG & 1) ? x0 : ex2_approx(x0), p1 = (DBG & 1) ? x1 : ex2_approx(x1);
+        float p0, p1;
+        if (att_poly_pair<DBG>(i)) exp2_poly2(x0, x1, p0, p1);
+        else { p0 = (DBG & 1) ? x0 : ex2_approx(x0); p1 = (DBG & 1) ? x1 : ex2_approx(x1); }
         acc_a = fadd2(acc_a, pack_f32x2(p0, p1));
         pk[i] = pack_bf16(p0, p1);
     }
@@ -67,22 +78,26 @@ __device__ __forceinline__ void exp_chunk(const uint32_t* r, uint32_t (&pk)[16],
     for (int i = 8; i < 16; ++i) {
         float x0, x1;
         unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, link_b), x0, x1);
-        const float p0 = (DBG & 1) ? x0 : ex2_approx(x0), p1 = (DBG & 1) ? x1 : ex2_approx(x1);
+        float p0, p1;
+        if (att_poly_pair<DBG>(i)) exp2_poly2(x0, x1, p0, p1);
+        else { p0 = (DBG & 1) ? x0 : ex2_approx(x0); p1 = (DBG & 1) ? x1 : ex2_approx(x1); }
         acc_b = fadd2(acc_b, pack_f32x2(p0, p1));
         pk[i] = pack_bf16(p0, p1);
     }
 }
 
 // diagnostic variant 32: CTA (0,0,0) appends (event << 56 | step << 48 | clock) records per warp behind the counters
-#define ATT_TRACE(ev, step) do { if (DBG == 32 && trace != nullptr && tr_n < 120) { trace[tr_n++] = (static_cast<long long>(ev) << 56) | (static_cast<long long>(step) << 48) | (clock64() & 0xFFFFFFFFFFFFll); } } while (0)
+#define ATT_TRACE(ev, step) do { if ((DBG & 32) && trace != nullptr && tr_n < 120) { trace[tr_n++] = (static_cast<long long>(ev) << 56) | (static_cast<long long>(step) << 48) | (clock64() & 0xFFFFFFFFFFFFll); } } while (0)
 
-template <int DBG>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int DBG, int NQ>
+__global__ void __launch_bounds__(AttCfg<NQ>::THREADS, 3 - NQ)
 attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                   // two tiles
-    uint8_t* sK = smem + 2 * ATT_TILE_BYTES;
+    using Cfg = AttCfg<NQ>;
+    constexpr int ATT_KV_STAGES = Cfg::KV_STAGES, ATT_W_TMA = Cfg::W_TMA, ATT_W_MMA = Cfg::W_MMA;
+    constexpr uint32_t ATT_TMEM_COLS = Cfg::TMEM_COLS, ATT_S_COL = Cfg::S_COL, ATT_O_COL = Cfg::O_COL, ATT_P_COL = Cfg::P_COL;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;                                   // NQ tiles
+    uint8_t* sK = smem + NQ * ATT_TILE_BYTES;
     uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_STAGES * ATT_TILE_BYTES);
     uint64_t* q_full = bars;
@@ -98,16 +113,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int head = blockIdx.y, copy = blockIdx.z;
-    const int q0 = blockIdx.x * 2 * ATT_TILE;
-    const int nq = (q0 + ATT_TILE < p.tokens) ? 2 : 1;    // query tiles of this block that hold valid rows
+    const int q0 = blockIdx.x * NQ * ATT_TILE;
+    const int nq = (NQ == 2 && q0 + ATT_TILE < p.tokens) ? 2 : 1;    // query tiles of this block that hold valid rows
     const int nkv = (p.tokens + ATT_TILE - 1) / ATT_TILE;
     const int hidden = p.heads * ATT_HD;
     long long* prof = nullptr;
-    if (DBG == 32) prof = p.prof + ((static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 44 + warp * 4;
+    if ((DBG & 32)) prof = p.prof + ((static_cast<long long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (4 * Cfg::THREADS / 32) + warp * 4;
     long long* trace = nullptr;
     int tr_n = 0;
-    if (DBG == 32 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0)
-        trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * 44 + warp * 128;
+    if ((DBG & 32) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0)
+        trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * (4 * Cfg::THREADS / 32) + warp * 128;
 
     if (warp == ATT_W_TMA && elect_one()) {
         tma_prefetch_desc(&tmQKV);
@@ -116,7 +131,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], nq);
         }
-        for (int x = 0; x < 2; ++x) {
+        for (int x = 0; x < NQ; ++x) {
             mbar_init(&s_full[x], 1);
             mbar_init(&s_free[x], 4);
             mbar_init(&p_ready[x], 4);
@@ -132,9 +147,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == ATT_W_TMA) {
-        if (elect_one()) {          // elect.sync: ptxas emits straight-line UTMALDG / UTCHMMA (no per-lane BRA.U.ANY loop)
-            if (DBG == 32 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)
-                trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * 44 + warp * 128;
+        if (!(DBG & 1024) && elect_one()) {          // elect.sync: ptxas emits straight-line UTMALDG / UTCHMMA (no per-lane BRA.U.ANY loop)
+            if ((DBG & 32) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)
+                trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * (4 * Cfg::THREADS / 32) + warp * 128;
             ATT_TRACE(0, 0);
             mbar_expect_tx(q_full, nq * ATT_TILE_BYTES);
             tma_load_3d(sQ, &tmQKV, q_full, head * ATT_HD, q0, copy);
@@ -152,9 +167,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     } else if (warp >= ATT_W_MMA) {
         // one issuer per query tile: the tiles' chains (S -> registers -> next S;  P -> P.V) stay independent of each other
         const int x = warp - ATT_W_MMA;
-        if (x < nq && elect_one()) {
-            if (DBG == 32 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)
-                trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * 44 + warp * 128;
+        if (!(DBG & 1024) && x < nq && elect_one()) {
+            if ((DBG & 32) && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)
+                trace = p.prof + static_cast<long long>(gridDim.x) * gridDim.y * gridDim.z * (4 * Cfg::THREADS / 32) + warp * 128;
             constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_TILE, ATT_HD, true);
             const uint32_t tS = tmem_base + ATT_S_COL + x * ATT_TILE;
             const uint32_t tO = tmem_base + ATT_O_COL + x * ATT_HD;
@@ -187,31 +202,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 umma_commit(&kv_empty[j % ATT_KV_STAGES]);              // this tile is done with K_j / V_j
             };
             long long pc_kv = 0, pc_p = 0, pc_f = 0, pc_t = 0, pc_start = 0;
-            if (DBG == 32) pc_start = clock64();
+            if ((DBG & 32)) pc_start = clock64();
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
             tc_fence_after();
             issue_s(0);
             for (int j = 0; j < nkv; ++j) {
                 if (j + 1 < nkv) {
-                    if (DBG == 32) pc_t = clock64();
+                    if ((DBG & 32)) pc_t = clock64();
                     mbar_wait(&kv_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
-                    if (DBG == 32) { const long long t = clock64(); pc_kv += t - pc_t; pc_t = t; }
+                    if ((DBG & 32)) { const long long t = clock64(); pc_kv += t - pc_t; pc_t = t; }
                     ATT_TRACE(1, j);
                     mbar_wait(&s_free[x], j & 1);                       // S_x(j) sits in the softmax warps' registers
                     tc_fence_after();
-                    if (DBG == 32) pc_f += clock64() - pc_t;
+                    if ((DBG & 32)) pc_f += clock64() - pc_t;
                     ATT_TRACE(2, j);
                     issue_s(j + 1);
+                    ATT_TRACE(4, j);
                 }
-                if (DBG == 32) pc_t = clock64();
+                if ((DBG & 32)) pc_t = clock64();
                 mbar_wait(&p_ready[x], j & 1);
                 tc_fence_after();
-                if (DBG == 32) pc_p += clock64() - pc_t;
+                if ((DBG & 32)) pc_p += clock64() - pc_t;
                 ATT_TRACE(3, j);
                 issue_pv(j);
+                ATT_TRACE(5, j);
             }
-            if (DBG == 32) { prof[0] = pc_kv; prof[1] = pc_p; prof[2] = clock64() - pc_start; prof[3] = pc_f; }
+            if ((DBG & 32)) { prof[0] = pc_kv; prof[1] = pc_p; prof[2] = clock64() - pc_start; prof[3] = pc_f; }
         }
     } else {
         const int x = warp >> 2;                          // query tile of this softmax warp group (warps 0-3: A, 4-7: B)
@@ -230,14 +247,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
             long long pc_wait = 0, pc_pass = 0, pc_tail = 0, pc_t = 0, pc_ld = 0, pc_max = 0, pc_pv = 0, pc_u = 0;
             for (int j = 0; j < nkv; ++j) {
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
-                if (DBG == 32) pc_t = clock64();
-                mbar_wait(&s_full[x], j & 1);
+                if ((DBG & 32)) pc_t = clock64();
+                if (!(DBG & 1024)) mbar_wait(&s_full[x], j & 1);
                 tc_fence_after();
-                if (DBG == 32) { const long long t = clock64(); pc_wait += t - pc_t; pc_t = t; }
+                if ((DBG & 32)) { const long long t = clock64(); pc_wait += t - pc_t; pc_t = t; }
                 ATT_TRACE(1, j);
                 // the whole score row into registers, then hand the S buffer back to the tensor pipe at once
                 uint32_t r[ATT_TILE];
-                if ((DBG & 7) != 4) {
+                if ((DBG & 3072) == 1024) {
+#pragma unroll
+                    for (int i = 0; i < ATT_TILE; ++i) r[i] = __float_as_uint(p.zero * (i + j) - 0.01f * (i + (lane & 7)));
+                } else if ((DBG & 7) != 4) {
                     if (nk == ATT_TILE) {
                         tmem_ld32(tS, r); tmem_ld32(tS + 32, r + 32); tmem_ld32(tS + 64, r + 64); tmem_ld32(tS + 96, r + 96);
                     } else {
@@ -253,13 +273,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                     }
                     tmem_wait_ld();
                 }
-                if (DBG == 32) { pc_u = clock64(); pc_ld += pc_u - pc_t; }
+                if ((DBG & 32)) { pc_u = clock64(); pc_ld += pc_u - pc_t; }
                 ATT_TRACE(2, j);
                 tc_fence_before();
                 __syncwarp();
-                if (elect_one()) mbar_arrive(&s_free[x]);
+                if (!(DBG & 1024) && elect_one()) mbar_arrive(&s_free[x]);
                 if ((DBG & 7) != 4) {
                     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                    if (!(DBG & 4096) || j == 0)
 #pragma unroll
                     for (int i = 0; i < ATT_TILE; i += 8) {
                         m0 = fmax3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
@@ -267,15 +288,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                         m2 = fmax3(m2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
                         m3 = fmax3(m3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
                     }
-                    const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                     if (j == 0) m_ref = mt;
-                    if (DBG == 32) { const long long t = clock64(); pc_max += t - pc_u; pc_u = t; }
+                    if ((DBG & 4096) && j > 0) mt = m_ref;
+                    if ((DBG & 32)) { const long long t = clock64(); pc_max += t - pc_u; pc_u = t; }
                     ATT_TRACE(3, j);
                     // lazy rescaling: the reference max is replaced (and O, l rescaled) only when this tile exceeds it by 2^8
                     const bool need = (mt - m_ref) * c > ATT_RESCALE_LOG2;
                     bool pv_waited = false;
                     if (__any_sync(0xffffffffu, need)) {
-                        if (j > 0) { mbar_wait(&pv_done[x], (j - 1) & 1); tc_fence_after(); pv_waited = true; }   // O_x is quiescent
+                        if (j > 0 && !(DBG & 1024)) { mbar_wait(&pv_done[x], (j - 1) & 1); tc_fence_after(); pv_waited = true; }   // O_x is quiescent
                         const float m_new = fmaxf(m_ref, mt);
                         const float sc = ex2_approx((m_ref - m_new) * c);
                         l2 = ffma2(l2, pack_f32x2(sc, sc), 0ull);
@@ -297,26 +319,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                     // from then on one group's load / max / wait phases fall into the other group's MUFU phase
                     // strict alternation of the exponential phases (both tiles valid): group x runs its MUFU phase j after
                     // the other group has finished its phase j (x = 1) / j - 1 (x = 0)
-                    if (ATT_ALTERNATE && nq == 2) {
+                    if ((DBG & 64) && nq == 2) {
                         if (x == 1) mbar_wait(&turn[0], j & 1);
                         else if (j > 0) mbar_wait(&turn[1], (j - 1) & 1);
                     }
+                    if ((DBG & 128) && nq == 2 && x == 1 && j == 0) mbar_wait(&turn[0], 0);
                     uint32_t pk[16];
                     exp_chunk<DBG>(r, pk, c2, nmc2, zero2, l2, l2b);
-                    if (DBG == 32) pc_u = clock64();
+                    if ((DBG & 32)) pc_u = clock64();
                     // P_x may only be overwritten once P_x(j-1) . V has retired (checked here, a quarter of the pass later)
-                    if (j > 0 && !pv_waited) { mbar_wait(&pv_done[x], (j - 1) & 1); tc_fence_after(); }
-                    if (DBG == 32) pc_pv += clock64() - pc_u;
+                    if (j > 0 && !pv_waited && !(DBG & 1024)) { mbar_wait(&pv_done[x], (j - 1) & 1); tc_fence_after(); }
+                    if ((DBG & 32)) pc_pv += clock64() - pc_u;
                     ATT_TRACE(4, j);
-                    if (DBG == 32 && j + 1 < nkv) { const bool rdy = mbar_try_wait(&s_full[x], (j + 1) & 1); ATT_TRACE(rdy ? 8 : 7, j); }
-                    tmem_st16(tP, pk);
+                    if ((DBG & 32) && j + 1 < nkv) { const bool rdy = mbar_try_wait(&s_full[x], (j + 1) & 1); ATT_TRACE(rdy ? 8 : 7, j); }
+                    if (!(DBG & 512) && (DBG & 3072) != 1024) tmem_st16(tP, pk); else asm volatile("" :: "r"(pk[0] ^ pk[5] ^ pk[9] ^ pk[15]));
                     exp_chunk<DBG>(r + 32, pk, c2, nmc2, zero2, l2, l2b);
-                    tmem_st16(tP + 16, pk);
+                    if (!(DBG & 512) && (DBG & 3072) != 1024) tmem_st16(tP + 16, pk); else asm volatile("" :: "r"(pk[0] ^ pk[5] ^ pk[9] ^ pk[15]));
                     exp_chunk<DBG>(r + 64, pk, c2, nmc2, zero2, l2, l2b);
-                    tmem_st16(tP + 32, pk);
+                    if (!(DBG & 512) && (DBG & 3072) != 1024) tmem_st16(tP + 32, pk); else asm volatile("" :: "r"(pk[0] ^ pk[5] ^ pk[9] ^ pk[15]));
                     exp_chunk<DBG>(r + 96, pk, c2, nmc2, zero2, l2, l2b);
-                    tmem_st16(tP + 48, pk);
-                    if (ATT_ALTERNATE && nq == 2) {
+                    if (!(DBG & 512) && (DBG & 3072) != 1024) tmem_st16(tP + 48, pk); else asm volatile("" :: "r"(pk[0] ^ pk[5] ^ pk[9] ^ pk[15]));
+                    if (((DBG & 64) && nq == 2) || ((DBG & 128) && nq == 2 && x == 0 && j == 0)) {
                         __syncwarp();
                         if (elect_one()) mbar_arrive(&turn[x]);
                     }
@@ -324,18 +347,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                     if (j > 0) { mbar_wait(&pv_done[x], (j - 1) & 1); tc_fence_after(); }
                     l2 = pack_f32x2(1.f, 0.f);
                 }
-                if (DBG == 32) { const long long t = clock64(); pc_pass += t - pc_t; pc_t = t; }
+                if ((DBG & 32)) { const long long t = clock64(); pc_pass += t - pc_t; pc_t = t; }
                 ATT_TRACE(5, j);
-                if (DBG == 32 && j + 1 < nkv) { const bool rdy = mbar_try_wait(&s_full[x], (j + 1) & 1); ATT_TRACE(rdy ? 10 : 9, j); }
+                if ((DBG & 32) && j + 1 < nkv) { const bool rdy = mbar_try_wait(&s_full[x], (j + 1) & 1); ATT_TRACE(rdy ? 10 : 9, j); }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (elect_one()) mbar_arrive(&p_ready[x]);
-                if (DBG == 32) { const long long t = clock64(); pc_tail += t - pc_t; pc_t = t; }
+                if (!(DBG & 1024) && elect_one()) mbar_arrive(&p_ready[x]);
+                if ((DBG & 32)) { const long long t = clock64(); pc_tail += t - pc_t; pc_t = t; }
                 ATT_TRACE(6, j);
             }
-            if (DBG == 32 && lane == 0) { prof[0] = pc_wait; prof[1] = pc_pass; prof[2] = pc_tail; prof[3] = (pc_ld << 42) | (pc_max << 21) | pc_pv; }
-            mbar_wait(&pv_done[x], (nkv - 1) & 1);
+            if ((DBG & 32) && lane == 0) { prof[0] = pc_wait; prof[1] = pc_pass; prof[2] = pc_tail; prof[3] = (pc_ld << 42) | (pc_max << 21) | pc_pv; }
+            if (!(DBG & 1024)) mbar_wait(&pv_done[x], (nkv - 1) & 1);
             tc_fence_after();
             const int q = q0 + x * ATT_TILE + row;
             float la, lb;
@@ -371,16 +394,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
 
 using namespace b200x;
 
-static int g_attn_dbg = 0;
+// production configuration: one query tile per CTA (two CTAs per SM) with a quarter of the exponentials on the FMA pipe
+// (variant bit 256); the other variants are diagnostics selected through the two b200x_debug_* setters below
+static int g_attn_dbg = 256;
+static int g_attn_nq = 1;
 
-template <int DBG>
+template <int DBG, int NQ = 2>
 static int launch_attention(const CUtensorMap& tm, const AttnParams& p, dim3 grid, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<DBG, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<NQ>::SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_kernel<DBG, NQ>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    attention_kernel<DBG><<<grid, ATT_THREADS, ATT_SMEM, s>>>(tm, p);
+    attention_kernel<DBG, NQ><<<grid, AttCfg<NQ>::THREADS, AttCfg<NQ>::SMEM, s>>>(tm, p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }
@@ -388,6 +415,7 @@ static int launch_attention(const CUtensorMap& tm, const AttnParams& p, dim3 gri
 // diagnostic only (not part of the public header): select a stripped-down variant of the kernel for bottleneck analysis
 static long long* g_attn_prof = nullptr;
 extern "C" void b200x_debug_attention_variant(int v) { g_attn_dbg = v; }
+extern "C" void b200x_debug_attention_tiles_per_cta(int nq) { g_attn_nq = nq; }
 // diagnostic variant 32 writes per-CTA cycle counters ([cta][10][4] long long) to this device buffer
 extern "C" void b200x_debug_attention_profile(void* d_buf) { g_attn_prof = static_cast<long long*>(d_buf); }
 
@@ -403,8 +431,20 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     const uint32_t box[3] = {ATT_HD, ATT_TILE, 1};
     B200X_TRY(make_tmap_bf16(&tm, d_qkv, 3, dims, strides, box));
     AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_prof, 0.0f};
-    dim3 grid(ceil_div(tokens, 2 * ATT_TILE), heads, copies);
+    dim3 grid(ceil_div(tokens, g_attn_nq * ATT_TILE), heads, copies);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (g_attn_nq == 1) {
+        switch (g_attn_dbg) {
+            case 0: return launch_attention<0, 1>(tm, p, grid, s);
+            case 32: return launch_attention<32, 1>(tm, p, grid, s);
+            case 256: return launch_attention<256, 1>(tm, p, grid, s);
+            case 8192: return launch_attention<8192, 1>(tm, p, grid, s);
+            case 16384: return launch_attention<16384, 1>(tm, p, grid, s);
+            case 4096: return launch_attention<4096, 1>(tm, p, grid, s);
+            case 4352: return launch_attention<4352, 1>(tm, p, grid, s);
+            default: return set_error(B200X_ERR_INVALID, "attention: unknown diagnostic variant %d for one tile per CTA", g_attn_dbg);
+        }
+    }
     switch (g_attn_dbg) {
         case 0: return launch_attention<0>(tm, p, grid, s);
         case 4: return launch_attention<4>(tm, p, grid, s);
@@ -413,6 +453,22 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
         case 28: return launch_attention<28>(tm, p, grid, s);
         case 1: return launch_attention<1>(tm, p, grid, s);
         case 32: return launch_attention<32>(tm, p, grid, s);
+        case 96: return launch_attention<96>(tm, p, grid, s);
+        case 24: return launch_attention<24>(tm, p, grid, s);
+        case 88: return launch_attention<88>(tm, p, grid, s);
+        case 120: return launch_attention<120>(tm, p, grid, s);
+        case 512: return launch_attention<512>(tm, p, grid, s);
+        case 1024: return launch_attention<1024>(tm, p, grid, s);
+        case 4096: return launch_attention<4096>(tm, p, grid, s);
+        case 4352: return launch_attention<4352>(tm, p, grid, s);
+        case 3072: return launch_attention<3072>(tm, p, grid, s);
+        case 576: return launch_attention<576>(tm, p, grid, s);
+        case 608: return launch_attention<608>(tm, p, grid, s);
+        case 64: return launch_attention<64>(tm, p, grid, s);
+        case 128: return launch_attention<128>(tm, p, grid, s);
+        case 256: return launch_attention<256>(tm, p, grid, s);
+        case 320: return launch_attention<320>(tm, p, grid, s);
+        case 384: return launch_attention<384>(tm, p, grid, s);
         default: return set_error(B200X_ERR_INVALID, "attention: unknown diagnostic variant %d", g_attn_dbg);
     }
 }

@@ -52,12 +52,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// mbarrier.try_wait with a suspend-time hint (like CUTLASS' ClusterBarrier::wait): the thread sleeps in hardware until the
+// phase completes (or the hint expires) instead of spinning through issue slots its SM sub-partition's math warps need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug traps (-> launch failure reported to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+#ifndef B200X_MBAR_HINT
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
     }
+#else
+    while (!mbar_try_wait_hint(bar, parity)) {
+        if (++spins > (1u << 16)) __trap();
+    }
+#endif
 }
 
 // ----------------------------------------------------------------------------- TMA

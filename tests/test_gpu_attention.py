@@ -18,12 +18,22 @@ def _ref(qkv, copies, tokens, heads):
 @pytest.mark.parametrize("copies,tokens,heads,scale", [
     (1, 128, 1, 1.0), (1, 64, 2, 1.0), (2, 272, 2, 1.0), (2, 1376, 6, 1.0), (1, 1376, 6, 6.0),
 ])
-def test_attention_matches_reference(copies, tokens, heads, scale):
+@pytest.mark.parametrize("tiles_per_cta,variant", [(1, 256), (1, 0), (2, 256), (2, 0)])
+def test_attention_matches_reference(copies, tokens, heads, scale, tiles_per_cta, variant):
+    # (1, 256) is the production configuration: one query tile per CTA, a quarter of the exponentials as an FMA-pipe polynomial
+    import ctypes
+    lib().b200x_debug_attention_tiles_per_cta(ctypes.c_int(tiles_per_cta))
+    lib().b200x_debug_attention_variant(ctypes.c_int(variant))
     g = torch.Generator(device="cpu").manual_seed(tokens + heads)
     qkv = (torch.randn(copies * tokens, 3 * heads * 64, generator=g) * scale).to(torch.bfloat16)
     ref = _ref(qkv, copies, tokens, heads)
     out = torch.full((copies * tokens, heads * 64), float("nan"), dtype=torch.bfloat16, device="cuda")
-    ok(lib().b200x_attention(P(D(qkv)), P(out), copies, tokens, heads, 64, P(None)))
+    try:
+        ok(lib().b200x_attention(P(D(qkv)), P(out), copies, tokens, heads, 64, P(None)))
+        torch.cuda.synchronize()
+    finally:
+        lib().b200x_debug_attention_tiles_per_cta(ctypes.c_int(1))
+        lib().b200x_debug_attention_variant(ctypes.c_int(256))
     got = out.float().cpu()
     assert torch.isfinite(got).all()
     err = (got - ref).abs().max().item()

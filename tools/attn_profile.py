@@ -15,7 +15,8 @@ n_cta = 6 * H * copies
 prof_all = torch.zeros(n_cta * 44 + 11 * 128, dtype=torch.int64, device="cuda")
 prof = prof_all[: n_cta * 44].view(n_cta, 11, 4)
 lib.b200x_debug_attention_profile(C.c_void_p(prof_all.data_ptr()))
-lib.b200x_debug_attention_variant(C.c_int(32))
+lib.b200x_debug_attention_tiles_per_cta(C.c_int(2))
+lib.b200x_debug_attention_variant(C.c_int(int(sys.argv[2]) if len(sys.argv) > 2 else 32))
 for _ in range(3):
     _lib.check(lib.b200x_attention(C.c_void_p(qkv.data_ptr()), C.c_void_p(att.data_ptr()), copies, T, H, 64, C.c_void_p(0)))
 torch.cuda.synchronize()
@@ -29,8 +30,8 @@ print(f"softmax: wait S {sm[..., 0].mean():9.0f}  pass {sm[..., 1].mean():9.0f} 
 packed = prof.cpu().view(copies * H, 6, 11, 4)[:, :5, 0:8, 3]
 ld, mx, pv = (packed >> 42).double().mean() / 11, ((packed >> 21) & 0x1FFFFF).double().mean() / 11, (packed & 0x1FFFFF).double().mean() / 11
 print(f"  inside pass per kv step: tmem load+wait {ld:6.0f}  s_free arrive + row max {mx:6.0f}  wait pv_done {pv:6.0f}  (rest = rescale check + exp + P stores)")
-for w in range(0):
-    print(f"  warp {w + 2}: wait {sm[:, :, w, 0].mean() / 11:7.0f} pass {sm[:, :, w, 1].mean() / 11:7.0f} tail {sm[:, :, w, 2].mean() / 11:7.0f}")
+for w in range(8):
+    print(f"  warp {w}: wait {sm[:, :, w, 0].mean() / 11:7.0f} pass {sm[:, :, w, 1].mean() / 11:7.0f} tail {sm[:, :, w, 2].mean() / 11:7.0f}")
 last = p.view(copies * H, 6, 11, 4)[:, 5]           # CTAs with ONE valid query tile (group A alone on the MUFU)
 sm1 = last[:, 0:4]
 print(f"single-tile CTAs: softmax wait {sm1[..., 0].mean() / 11:7.0f} pass {sm1[..., 1].mean() / 11:7.0f} tail {sm1[..., 2].mean() / 11:7.0f} per kv step;"

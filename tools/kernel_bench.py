@@ -66,7 +66,8 @@ def gemm(a, lda, w, ldw, m, n, k, bn, out, ldc, mode, bias, gelu, resid):
 print(f"copies={copies}  M={M}")
 if os.environ.get("KB_ATTN_VARIANTS"):
     import ctypes
-    for v in (0, 1, 4, 4 + 8, 4 + 16, 4 + 8 + 16):
+    lib.b200x_debug_attention_tiles_per_cta(ctypes.c_int(int(os.environ.get('KB_ATTN_NQ', '2'))))
+    for v in [int(t) for t in os.environ.get('KB_ATTN_LIST', '0,1,4,12,20,28').split(',')]:
         lib.b200x_debug_attention_variant(ctypes.c_int(v))
         timeit(lambda: _lib.check(lib.b200x_attention(P(qkv), P(att), copies, T, H, 64, P(None))), flops=4 * copies * H * T * T * 64, name=f"attention variant {v}")
     sys.exit(0)
