@@ -390,6 +390,254 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     if (warp == ATT_W_MMA) tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
 }
 
+
+// ----------------------------------------------------------------------------- split-row kernel (production)
+// One 128-row query tile per CTA, two CTAs per SM, and TWO threads per query row: softmax warp w (0-7) owns TMEM lanes
+// [32 (w & 3), +32) and the score columns [64 (w >> 2), +64) of every 128-key tile, so each SM sub-partition holds four
+// softmax warps (two per CTA) with short phases instead of two with long ones - the MUFU sees exponential work from
+// several warps at once and one warp's load / max / barrier latencies hide behind the others'.
+//   warps 0-7 : softmax (row = 32 (w & 3) + lane, half = w >> 2);  warp 8: TMA producer;  warp 9: tcgen05.mma issuer
+// The two threads of a row agree on the tile's row max through shared memory (bf16, 512 B) and one named barrier per
+// row quarter; the running reference max is lazily replaced exactly as in the kernel above.  Each thread keeps the partial
+// row sum of its own columns and normalises / stores its own 32 output columns; the partial sums meet once, at the end.
+// TMEM columns: S [0,128)  O [128,192)  P [192,256).
+struct AttSplit {
+    static constexpr int THREADS = 320, W_TMA = 8, W_MMA = 9, KV_STAGES = 3;
+    static constexpr int BAR_BYTES = 256, XCH_BYTES = 512;
+    static constexpr int SMEM = ATT_TILE_BYTES * (1 + 2 * KV_STAGES) + BAR_BYTES + XCH_BYTES;
+    static constexpr uint32_t TMEM_COLS = 256, S_COL = 0, O_COL = 128, P_COL = 192;
+};
+
+// rendezvous of the two warps that share a row quarter (named barriers 1-4, compile-time ids)
+__device__ __forceinline__ void pair_bar_sync(int quarter) {
+    switch (quarter) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
+
+template <int DBG>
+__global__ void __launch_bounds__(AttSplit::THREADS, 2)
+attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
+    using Cfg = AttSplit;
+    constexpr int STAGES = Cfg::KV_STAGES;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + ATT_TILE_BYTES;
+    uint8_t* sV = sK + STAGES * ATT_TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + STAGES;
+    uint64_t* s_full = kv_empty + STAGES;                 // S(j) is in TMEM
+    uint64_t* s_free = s_full + 1;                        // the softmax warps hold S(j) in registers: S(j+1) may be issued
+    uint64_t* p_ready = s_free + 1;                       // P(j) is in TMEM
+    uint64_t* pv_done = p_ready + 1;                      // O += P(j) V_j has retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    __nv_bfloat16* xch = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);   // [2][128] tile row max per half
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int head = blockIdx.y, copy = blockIdx.z;
+    const int q0 = blockIdx.x * ATT_TILE;
+    const int nkv = (p.tokens + ATT_TILE - 1) / ATT_TILE;
+    const int hidden = p.heads * ATT_HD;
+
+    if (warp == Cfg::W_TMA && elect_one()) {
+        tma_prefetch_desc(&tmQKV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 8);
+        mbar_init(p_ready, 8);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == Cfg::W_MMA) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == Cfg::W_TMA) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, ATT_TILE_BYTES);
+            tma_load_3d(sQ, &tmQKV, q_full, head * ATT_HD, q0, copy);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j % STAGES;
+                mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
+                tma_load_3d(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], hidden + head * ATT_HD, j * ATT_TILE, copy);
+                tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * hidden + head * ATT_HD, j * ATT_TILE, copy);
+            }
+        }
+    } else if (warp == Cfg::W_MMA) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_TILE, ATT_HD, true);
+            const uint32_t tS = tmem_base + Cfg::S_COL, tO = tmem_base + Cfg::O_COL, tP = tmem_base + Cfg::P_COL;
+            const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+            const uint64_t k_desc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t v_desc0 = make_smem_desc_sw128(smem_u32(sV), 16384, 1024);
+            auto issue_s = [&](int j) {                   // S = Q K_j^T
+                const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
+                const uint32_t idesc_s = make_idesc_bf16(ATT_TILE, nk, false);
+                const uint64_t kd = k_desc0 + static_cast<uint64_t>((j % STAGES) * (ATT_TILE_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, q_desc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(s_full);
+            };
+            auto issue_pv = [&](int j) {                  // O += P V_j
+                const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
+                const uint64_t vd = v_desc0 + static_cast<uint64_t>((j % STAGES) * (ATT_TILE_BYTES >> 4));
+                if (nk == ATT_TILE) {
+#pragma unroll
+                    for (int ks = 0; ks < ATT_TILE / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                } else {
+                    for (int ks = 0; ks < nk / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                }
+                umma_commit(pv_done);
+                umma_commit(&kv_empty[j % STAGES]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < nkv; ++j) {
+                if (j + 1 < nkv) {
+                    mbar_wait(&kv_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
+                    mbar_wait(s_free, j & 1);
+                    tc_fence_after();
+                    issue_s(j + 1);
+                }
+                mbar_wait(p_ready, j & 1);
+                tc_fence_after();
+                issue_pv(j);
+            }
+        }
+    } else {
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t tS = t_lane + Cfg::S_COL + half * 64;
+        const uint32_t tO = t_lane + Cfg::O_COL + half * 32;
+        const uint32_t tP = t_lane + Cfg::P_COL + half * 32;
+        const float c = p.scale_log2;
+        const uint64_t c2 = pack_f32x2(c, c);
+        const uint64_t zero2 = pack_f32x2(p.zero, p.zero);
+        float m_ref = -INFINITY;
+        uint64_t l2 = 0ull, l2b = 0ull;
+        for (int j = 0; j < nkv; ++j) {
+            const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE) - half * 64;    // valid columns of this thread's half (may be <= 0)
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t r[64];
+            if (nk >= 64) {
+                tmem_ld32(tS, r);
+                tmem_ld32(tS + 32, r + 32);
+            } else {
+#pragma unroll
+                for (int col = 0; col < 64; col += 16) {
+                    if (col < nk) {
+                        tmem_ld16(tS + col, r + col);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[col + i] = 0xff800000u;   // -inf: exp2 -> 0, never read by P.V
+                    }
+                }
+            }
+            tmem_wait_ld();
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+                m0 = fmax3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                m1 = fmax3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                m2 = fmax3(m2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+                m3 = fmax3(m3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+            }
+            // the pair's common view of the tile's row max: both halves rounded UP to bf16 (so the reference never lies
+            // below a score by more than the lazy-rescale slack), exchanged through shared memory
+            const __nv_bfloat16 m_loc_b = __float2bfloat16_ru(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+            xch[half * 128 + row] = m_loc_b;
+            pair_bar_sync(quarter);
+            const float mt = fmaxf(__bfloat162float(m_loc_b), __bfloat162float(xch[(half ^ 1) * 128 + row]));
+            // S(j) is released only now: s_free(j) completing then also means that all eight warps have read this tile's
+            // exchange slots, so the writes of tile j + 1 (which follow s_full(j + 1)) cannot overtake a read of tile j
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(s_free);
+            if (j == 0) m_ref = mt;
+            const bool need = (mt - m_ref) * c > ATT_RESCALE_LOG2;
+            bool pv_waited = false;
+            if (__any_sync(0xffffffffu, need)) {
+                if (j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); pv_waited = true; }   // O is quiescent
+                const float m_new = fmaxf(m_ref, mt);
+                const float sc = ex2_approx((m_ref - m_new) * c);
+                l2 = ffma2(l2, pack_f32x2(sc, sc), 0ull);
+                l2b = ffma2(l2b, pack_f32x2(sc, sc), 0ull);
+#pragma unroll
+                for (int cidx = 0; cidx < 32; cidx += 16) {
+                    uint32_t o[16];
+                    tmem_ld16(tO + cidx, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                    tmem_st16(tO + cidx, o);
+                }
+                m_ref = m_new;
+            }
+            const float mc = m_ref * c;
+            const uint64_t nmc2 = pack_f32x2(-mc, -mc);
+            uint32_t pk[16];
+            exp_chunk<DBG>(r, pk, c2, nmc2, zero2, l2, l2b);
+            if (j > 0 && !pv_waited) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }   // P(j-1) . V has retired
+            tmem_st16(tP, pk);
+            exp_chunk<DBG>(r + 32, pk, c2, nmc2, zero2, l2, l2b);
+            tmem_st16(tP + 16, pk);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(p_ready);
+        }
+        mbar_wait(pv_done, (nkv - 1) & 1);
+        tc_fence_after();
+        // the two partial row sums meet in the (now idle) first K stage
+        float la, lb;
+        unpack_f32x2(fadd2(l2, l2b), la, lb);
+        float* lx = reinterpret_cast<float*>(sK);
+        lx[half * 128 + row] = la + lb;
+        pair_bar_sync(quarter);
+        const float inv = 1.0f / (la + lb + lx[(half ^ 1) * 128 + row]);
+        const int q = q0 + row;
+        uint4 packed[4];
+#pragma unroll
+        for (int cidx = 0; cidx < 32; cidx += 16) {
+            uint32_t o[16];
+            tmem_ld16(tO + cidx, o);
+            tmem_wait_ld();
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                w[i] = pack_bf16(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+            packed[cidx / 8] = make_uint4(w[0], w[1], w[2], w[3]);
+            packed[cidx / 8 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        if (q < p.tokens) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(copy) * p.tokens + q) * hidden + head * ATT_HD + half * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = packed[i];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == Cfg::W_MMA) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
 }  // namespace b200x
 
 using namespace b200x;
@@ -408,6 +656,19 @@ static int launch_attention(const CUtensorMap& tm, const AttnParams& p, dim3 gri
         configured = true;
     }
     attention_kernel<DBG, NQ><<<grid, AttCfg<NQ>::THREADS, AttCfg<NQ>::SMEM, s>>>(tm, p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+template <int DBG>
+static int launch_attention_split(const CUtensorMap& tm, const AttnParams& p, dim3 grid, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_split_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSplit::SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_split_kernel<DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    attention_split_kernel<DBG><<<grid, AttSplit::THREADS, AttSplit::SMEM, s>>>(tm, p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }
@@ -431,8 +692,16 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     const uint32_t box[3] = {ATT_HD, ATT_TILE, 1};
     B200X_TRY(make_tmap_bf16(&tm, d_qkv, 3, dims, strides, box));
     AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_prof, 0.0f};
-    dim3 grid(ceil_div(tokens, g_attn_nq * ATT_TILE), heads, copies);
+    dim3 grid(ceil_div(tokens, (g_attn_nq > 0 ? g_attn_nq : 1) * ATT_TILE), heads, copies);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (g_attn_nq == 0) {                                  // split-row kernel: one tile per CTA, two threads per query row
+        grid.x = ceil_div(tokens, ATT_TILE);
+        switch (g_attn_dbg) {
+            case 0: return launch_attention_split<0>(tm, p, grid, s);
+            case 256: return launch_attention_split<256>(tm, p, grid, s);
+            default: return set_error(B200X_ERR_INVALID, "attention: unknown diagnostic variant %d for the split-row kernel", g_attn_dbg);
+        }
+    }
     if (g_attn_nq == 1) {
         switch (g_attn_dbg) {
             case 0: return launch_attention<0, 1>(tm, p, grid, s);
