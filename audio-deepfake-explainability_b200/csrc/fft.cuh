@@ -32,6 +32,42 @@ constexpr float kS32[16] = {0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.
                             1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
                             0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
 
+
+// Per-lane trigonometry for the frame pre / post passes.  Bin k = lane + 32 r and sample pair (2m, 2m+1), m = lane + 32 r,
+// both factor into a per-lane angle and a per-r angle whose cos / sin are compile-time constants after unrolling, so
+//   e^(i 2 pi k / 2048)        = e^(i 2 pi lane / 2048) . e^(i 2 pi r / 64)
+//   hann(n) = 1/2 - 1/2 cos(2 pi n / 2048),  cos(2 pi (2m + j) / 2048) = Re[e^(i 2 pi (2 lane + j) / 2048) . e^(i 2 pi r / 32)]
+// cost 2-4 FMAs per value instead of a table load per value: the 64 loads per frame and lane (twiddle + window) were
+// the top stall of the iSTFT / mel kernels (ncu: 44-54 % of samples on the long scoreboard at their first consumer).
+// (constant memory: with the loops unrolled the index is an immediate, so each value is a constant-bank FMA operand)
+static __constant__ float c_cos64[32] = {1.0f, 0.995184727f, 0.98078528f, 0.956940336f, 0.923879533f, 0.881921264f, 0.831469612f, 0.773010453f, 0.707106781f, 0.634393284f, 0.555570233f, 0.471396737f, 0.382683432f, 0.290284677f, 0.195090322f, 0.0980171403f, 0.0f, -0.0980171403f, -0.195090322f, -0.290284677f, -0.382683432f, -0.471396737f, -0.555570233f, -0.634393284f, -0.707106781f, -0.773010453f, -0.831469612f, -0.881921264f, -0.923879533f, -0.956940336f, -0.98078528f, -0.995184727f};
+static __constant__ float c_sin64[32] = {0.0f, 0.0980171403f, 0.195090322f, 0.290284677f, 0.382683432f, 0.471396737f, 0.555570233f, 0.634393284f, 0.707106781f, 0.773010453f, 0.831469612f, 0.881921264f, 0.923879533f, 0.956940336f, 0.98078528f, 0.995184727f, 1.0f, 0.995184727f, 0.98078528f, 0.956940336f, 0.923879533f, 0.881921264f, 0.831469612f, 0.773010453f, 0.707106781f, 0.634393284f, 0.555570233f, 0.471396737f, 0.382683432f, 0.290284677f, 0.195090322f, 0.0980171403f};
+static __constant__ float c_cos32[32] = {1.0f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f, 0.382683432f, 0.195090322f, 0.0f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f, -1.0f, -0.98078528f, -0.923879533f, -0.831469612f, -0.707106781f, -0.555570233f, -0.382683432f, -0.195090322f, 0.0f, 0.195090322f, 0.382683432f, 0.555570233f, 0.707106781f, 0.831469612f, 0.923879533f, 0.98078528f};
+static __constant__ float c_sin32[32] = {0.0f, 0.195090322f, 0.382683432f, 0.555570233f, 0.707106781f, 0.831469612f, 0.923879533f, 0.98078528f, 1.0f, 0.98078528f, 0.923879533f, 0.831469612f, 0.707106781f, 0.555570233f, 0.382683432f, 0.195090322f, 0.0f, -0.195090322f, -0.382683432f, -0.555570233f, -0.707106781f, -0.831469612f, -0.923879533f, -0.98078528f, -1.0f, -0.98078528f, -0.923879533f, -0.831469612f, -0.707106781f, -0.555570233f, -0.382683432f, -0.195090322f};
+
+struct LaneTrig {
+    float2 tw;      // e^(i 2 pi lane / 2048)
+    float2 h0, h1;  // 1/2 e^(i 2 pi (2 lane) / 2048), 1/2 e^(i 2 pi (2 lane + 1) / 2048)
+};
+__device__ __forceinline__ LaneTrig lane_trig(int lane) {
+    LaneTrig t;
+    t.tw = g_tw2048[lane];
+    const float2 a = g_tw2048[2 * lane], b = g_tw2048[2 * lane + 1];
+    t.h0 = make_float2(0.5f * a.x, 0.5f * a.y);
+    t.h1 = make_float2(0.5f * b.x, 0.5f * b.y);
+    return t;
+}
+// (cos, sin)(2 pi (lane + 32 r) / 2048)
+__device__ __forceinline__ float2 twiddle2048(const LaneTrig& t, int r) {
+    const float cr = c_cos64[r], sr = c_sin64[r];
+    return make_float2(fmaf(t.tw.x, cr, -t.tw.y * sr), fmaf(t.tw.y, cr, t.tw.x * sr));
+}
+// periodic Hann(2048) at samples 2m and 2m + 1, m = lane + 32 r
+__device__ __forceinline__ float2 hann_pair(const LaneTrig& t, int r) {
+    const float cr = c_cos32[r], sr = c_sin32[r];
+    return make_float2(fmaf(t.h0.y, sr, fmaf(-t.h0.x, cr, 0.5f)), fmaf(t.h1.y, sr, fmaf(-t.h1.x, cr, 0.5f)));
+}
+
 template <bool INV, int K, int J, int M>
 __device__ __forceinline__ void fft32_bfly(float2 (&t)[32]) {
     constexpr int H = M / 2;
