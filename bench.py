@@ -57,27 +57,34 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.rows, self._proc, self._t = index, [], None, None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        for line in self._proc.stdout:                       # one line per 20 ms sample from ONE long-running nvidia-smi
+            cells = [c.strip() for c in line.strip().split(",")]
+            if len(cells) >= 6:
+                self.rows.append(cells)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+            time.sleep(0.15)                                 # first sample is in before the timed region starts
+            self.rows.clear()
+        except Exception:
+            self._proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+            self._t.join(timeout=5)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -296,17 +303,34 @@ def run_engine(args):
     n_pass = max(1, min(args.steps, 3))
     total_ms = sum(v[0] for v in tim.values())
     shares = {k: (v[0] / total_ms if total_ms else 0.0) for k, v in tim.items()}
-    dom = max(("attention", "gemm"), key=lambda k: tim[k][0])
+    # the dominant KERNEL is the fused attention kernel (one launch per layer; the "gemm" class is four different problems)
+    dom = "attention"
     evals_timed = (n_win + 1) * n_pass
-    flops = (FLOP_ATTN_PER_EVAL if dom == "attention" else FLOP_GEMM_PER_EVAL) * evals_timed
+    flops = FLOP_ATTN_PER_EVAL * evals_timed
     dom_ms, dom_n = tim[dom]
     achieved = flops / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0
-    roofline = {"bound": "tensor", "kernel": "attention_kernel" if dom == "attention" else "gemm_bf16_tn_kernel",
+    gemm_ms = tim["gemm"][0]
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (profiles/): measured on the
+    # 228-copy sweep launches; the baseline (1 copy) launches of the same kernel are scaled by their copy count so that the
+    # figure is an average per launch over the same launches as `achieved`
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_j_ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            t = json.load(f).get("attention_kernel")
+        if t:
+            traffic = t["traffic_bytes_per_launch"] * (n_win + 1) / n_win / 2.0
+            traffic_src = "profiles/r01_j_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of bench.py)"
+    roofline = {"bound": "tensor", "kernel": "attention_kernel",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": (n_win + 1) / 2.0 * 1376 * (1152 + 384) * 2,
                 "peak_source": f"{peaks['source']} (sustained bf16; kernel timed inside a long step)",
                 "avg_launch_ms": dom_ms / dom_n if dom_n else None, "launches": dom_n,
                 "algorithmic_flops_per_launch": flops / dom_n if dom_n else None,
+                "gemm_class": {"achieved": FLOP_GEMM_PER_EVAL * evals_timed / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
+                               "unit": "TFLOP/s", "launches": tim["gemm"][1],
+                               "frac": (FLOP_GEMM_PER_EVAL * evals_timed / (gemm_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]) if gemm_ms else None},
                 "share_of_step": shares, "ms_per_class": {k: v[0] / n_pass for k, v in tim.items()},
                 "whole_forward_frac_of_peak": (FLOP_PER_EVAL * evals_per_step / world * args.steps / (ms_dev * 1e-3) / 1e12)
                 / peaks["bf16_tflops_sustained"]}
