@@ -562,9 +562,14 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) 
             // the pair's common view of the tile's row max: both halves rounded UP to bf16 (so the reference never lies
             // below a score by more than the lazy-rescale slack), exchanged through shared memory
             const __nv_bfloat16 m_loc_b = __float2bfloat16_ru(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-            xch[half * 128 + row] = m_loc_b;
-            pair_bar_sync(quarter);
-            const float mt = fmaxf(__bfloat162float(m_loc_b), __bfloat162float(xch[(half ^ 1) * 128 + row]));
+            float mt;
+            if (DBG & 2) {                                  // diagnostic: no exchange (numerically wrong, timing only)
+                mt = __bfloat162float(m_loc_b);
+            } else {
+                xch[half * 128 + row] = m_loc_b;
+                pair_bar_sync(quarter);
+                mt = fmaxf(__bfloat162float(m_loc_b), __bfloat162float(xch[(half ^ 1) * 128 + row]));
+            }
             // S(j) is released only now: s_free(j) completing then also means that all eight warps have read this tile's
             // exchange slots, so the writes of tile j + 1 (which follow s_full(j + 1)) cannot overtake a read of tile j
             tc_fence_before();
@@ -699,6 +704,8 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
         switch (g_attn_dbg) {
             case 0: return launch_attention_split<0>(tm, p, grid, s);
             case 256: return launch_attention_split<256>(tm, p, grid, s);
+            case 258: return launch_attention_split<258>(tm, p, grid, s);
+            case 16386: return launch_attention_split<16386>(tm, p, grid, s);
             default: return set_error(B200X_ERR_INVALID, "attention: unknown diagnostic variant %d for the split-row kernel", g_attn_dbg);
         }
     }

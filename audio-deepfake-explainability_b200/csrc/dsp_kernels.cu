@@ -26,6 +26,7 @@ constexpr int DSP_WARPS = 4;                    // warps per CTA for the FFT ker
 constexpr int DSP_THREADS = DSP_WARPS * 32;
 constexpr int DSP_SMEM = (DSP_WARPS * FFT_TILE + FFT_TWIDDLE) * 8;
 constexpr int ISTFT_ROW = 1026;                 // float2 elements copied per spectrogram row (1025 bins + 1: 16-byte multiple)
+constexpr int MEL_SMEM = DSP_SMEM + DSP_WARPS * 2048 * 4 + DSP_WARPS * 8;   // + one staged 2048-sample frame and one mbarrier per warp
 constexpr int ISTFT_SMEM = DSP_SMEM + DSP_WARPS * 2 * ISTFT_ROW * 8 + DSP_WARPS * 2 * 8;
 
 __global__ void init_tables_kernel() {
@@ -300,7 +301,7 @@ struct MelParams {
     const int* frame_range;    // optional [copies][2] = [ma, mb): only these frames are computed
 };
 
-__global__ void __launch_bounds__(DSP_THREADS, 4)      // 128 registers: four CTAs per SM hide the frame loads' latency
+__global__ void __launch_bounds__(DSP_THREADS, 3)      // 168 registers, 74 KB of shared memory: three CTAs per SM
 mel_db_kernel(MelParams p) {
     extern __shared__ __align__(16) float2 dsp_smem[];
     __shared__ float s_max[DSP_WARPS];
@@ -323,10 +324,49 @@ mel_db_kernel(MelParams p) {
     if (p.frame_range != nullptr) { f_lo = p.frame_range[2 * copy]; f_hi = p.frame_range[2 * copy + 1]; }
     const int f_begin = f_lo + blockIdx.x * p.frames_per_cta;
     const int f_end = min(f_begin + p.frames_per_cta, f_hi);
+    // Interior frames (2048 contiguous, 16-byte aligned samples) are staged through shared memory with a 1-D TMA bulk copy
+    // per warp: the copy of the warp's NEXT frame is issued as soon as the current one sits in registers and lands during
+    // the FFT, so the load stage no longer waits on L2 latency.  Edge frames (reflect padding) take the direct path.
+    float* fbuf = reinterpret_cast<float*>(dsp_smem + DSP_WARPS * FFT_TILE + FFT_TWIDDLE) + warp * NFFT;
+    uint64_t* fbar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(dsp_smem + DSP_WARPS * FFT_TILE + FFT_TWIDDLE) + DSP_WARPS * NFFT) + warp;
+    const bool can_stage = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    auto interior_of = [&](int t) {
+        const long long b = static_cast<long long>(t) * HOP - NFFT / 2;
+        return b >= 0 && b + NFFT <= p.n_samples;
+    };
+    if (lane == 0) {
+        mbar_init(fbar, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    bool pending = false;
+    uint32_t staged = 0;
+    {
+        const int t0 = f_begin + warp;
+        if (t0 < f_end && can_stage && interior_of(t0)) {
+            pending = true;
+            if (lane == 0) {
+                mbar_expect_tx(fbar, NFFT * 4);
+                bulk_load_1d(fbuf, y + static_cast<long long>(t0) * HOP - NFFT / 2, NFFT * 4, fbar);
+            }
+        }
+    }
     for (int t = f_begin + warp; t < f_end; t += DSP_WARPS) {
         const long long base = static_cast<long long>(t) * HOP - NFFT / 2;
         float2 v[32];
         const bool interior = (base >= 0) && (base + NFFT <= p.n_samples);
+        if (pending) {
+            mbar_wait(fbar, staged & 1);
+            ++staged;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const int m = lane + 32 * r;
+                const float2 s = *reinterpret_cast<const float2*>(fbuf + 2 * m);
+                const float2 w = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
+                v[r] = make_float2(s.x * gain * w.x, s.y * gain * w.y);
+            }
+            __syncwarp();                              // every lane has read the buffer: it may be refilled
+        } else {
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
             const int m = lane + 32 * r;
@@ -343,6 +383,15 @@ mel_db_kernel(MelParams p) {
             }
             const float2 w = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
             v[r] = make_float2(s.x * gain * w.x, s.y * gain * w.y);
+        }
+        }
+        {
+            const int tn = t + DSP_WARPS;
+            pending = tn < f_end && can_stage && interior_of(tn);
+            if (pending && lane == 0) {
+                mbar_expect_tx(fbar, NFFT * 4);
+                bulk_load_1d(fbuf, y + static_cast<long long>(tn) * HOP - NFFT / 2, NFFT * 4, fbar);
+            }
         }
         fft1024_warp<false>(v, tile, tw, lane);
         float2 X[32], xn;
@@ -673,7 +722,7 @@ extern "C" int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_sample
     B200X_TRY(ensure_tables(s));
     B200X_TRY(ensure_melbank(sample_rate, n_mels, f_min, f_max));
     static bool cfg = false;
-    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DSP_SMEM)); cfg = true; }
+    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEL_SMEM)); cfg = true; }
     MelParams p;
     p.y = d_y; p.y_stride = y_stride; p.n_samples = n_samples; p.sumsq = d_sumsq; p.ref_rms = ref_rms; p.rms_count = rms_count;
     p.n_frames = 1 + static_cast<int>(n_samples / HOP); p.n_mels = n_mels;
@@ -683,7 +732,7 @@ extern "C" int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_sample
     const int span = d_frame_range ? std::min(p.n_frames, std::max(1, max_range_frames)) : p.n_frames;
     B200X_REQUIRE(db_frames >= span, "mel: db_frames=%d smaller than the frame span %d", db_frames, span);
     dim3 grid(ceil_div(span, p.frames_per_cta), copies);
-    mel_db_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(p);
+    mel_db_kernel<<<grid, DSP_THREADS, MEL_SMEM, s>>>(p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }

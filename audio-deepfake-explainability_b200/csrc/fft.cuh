@@ -126,21 +126,27 @@ __device__ __forceinline__ void fft_fill_twiddles(float2* tw) {
 
 template <bool INV>
 __device__ __forceinline__ void fft1024_warp(float2 (&v)[32], float2* tile, const float2* tw, int lane) {
-    fft32<INV>(v);                                     // over n2 (lane = n1): v[k2]
+    // ONE copy of the unrolled 32-point FFT in the instruction stream, executed twice: the fully inlined form of the frame
+    // kernels was ~50 KB of code, past the instruction cache (ncu: 25 % of the mel kernel's samples were "no instruction")
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        fft32<INV>(v);                                 // pass 0: over n2 (lane = n1): v[k2];  pass 1: over n1 (lane = k2): v[k1] = X[32 k1 + k2]
+        if (pass == 0) {
 #pragma unroll
-    for (int k2 = 1; k2 < 32; ++k2) {                  // times W_1024^(n1 k2)
-        const float2 w = tw[k2 * 32 + lane];
-        const float wi = INV ? w.y : -w.y;
-        const float2 x = v[k2];
-        v[k2] = make_float2(x.x * w.x - x.y * wi, x.x * wi + x.y * w.x);
+            for (int k2 = 1; k2 < 32; ++k2) {          // times W_1024^(n1 k2)
+                const float2 w = tw[k2 * 32 + lane];
+                const float wi = INV ? w.y : -w.y;
+                const float2 x = v[k2];
+                v[k2] = make_float2(x.x * w.x - x.y * wi, x.x * wi + x.y * w.x);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) tile[k2 * 33 + lane] = v[k2];
+            __syncwarp();
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[n1] = tile[lane * 33 + n1];
+        }
     }
-    __syncwarp();
-#pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) tile[k2 * 33 + lane] = v[k2];
-    __syncwarp();
-#pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1) v[n1] = tile[lane * 33 + n1];
-    fft32<INV>(v);                                     // over n1 (lane = k2): v[k1] = X[32 k1 + k2]
 }
 
 }  // namespace b200x
