@@ -213,6 +213,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                     mbar_wait(&kv_full[(j + 1) % ATT_KV_STAGES], ((j + 1) / ATT_KV_STAGES) & 1);
                     if ((DBG & 32)) { const long long t = clock64(); pc_kv += t - pc_t; pc_t = t; }
                     ATT_TRACE(1, j);
+                    if (DBG & 32768) mbar_spin_wait(&s_free[x], j & 1); else
                     mbar_wait(&s_free[x], j & 1);                       // S_x(j) sits in the softmax warps' registers
                     tc_fence_after();
                     if ((DBG & 32)) pc_f += clock64() - pc_t;
@@ -221,6 +222,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                     ATT_TRACE(4, j);
                 }
                 if ((DBG & 32)) pc_t = clock64();
+                if (DBG & 32768) mbar_spin_wait(&p_ready[x], j & 1); else
                 mbar_wait(&p_ready[x], j & 1);
                 tc_fence_after();
                 if ((DBG & 32)) pc_p += clock64() - pc_t;
@@ -714,6 +716,7 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
             case 0: return launch_attention<0, 1>(tm, p, grid, s);
             case 32: return launch_attention<32, 1>(tm, p, grid, s);
             case 256: return launch_attention<256, 1>(tm, p, grid, s);
+            case 33024: return launch_attention<33024, 1>(tm, p, grid, s);
             case 8192: return launch_attention<8192, 1>(tm, p, grid, s);
             case 16384: return launch_attention<16384, 1>(tm, p, grid, s);
             case 4096: return launch_attention<4096, 1>(tm, p, grid, s);

@@ -42,6 +42,7 @@ __global__ void init_tables_kernel() {
             acc += w * w;
         }
         g_wss512[i] = acc;
+        g_rwss512[i] = static_cast<float>(1.0 / static_cast<double>(acc));
     }
 }
 
@@ -139,6 +140,9 @@ struct IstftParams {
                               // only the samples those frames read are synthesised (iSTFT linearity)
 };
 
+// MODE is a template parameter: the mask is evaluated per bin inside the fully unrolled load stage, and a run-time mode
+// cost an ISETP / BRA pair per element there (ncu: a quarter of the kernel's samples sat in that stage)
+template <int MODE>
 __global__ void __launch_bounds__(DSP_THREADS)
 istft_masked_kernel(IstftParams p) {
     extern __shared__ __align__(16) float2 dsp_smem[];
@@ -160,11 +164,11 @@ istft_masked_kernel(IstftParams p) {
     const int hp_b = min(hp_a + p.hops_per_strip, h_hi + 1);
     if (hp_a >= hp_b) return;
     int t0 = 0, t1 = 0, f0 = 0, f1 = 0;
-    if (p.mode == 1 || p.mode == 3) {
+    if (MODE == 1 || MODE == 3) {
         const int4 w = *reinterpret_cast<const int4*>(p.windows + 4 * copy);
         t0 = w.x; t1 = w.y; f0 = w.z; f1 = w.w;
     }
-    const float* gain = p.mode == 2 ? p.gains + static_cast<long long>(copy) * NBIN : nullptr;
+    const float* gain = MODE == 2 ? p.gains + static_cast<long long>(copy) * NBIN : nullptr;
     float* yout = p.y + static_cast<long long>(copy) * p.out_stride;
 
     const LaneTrig trig = lane_trig(lane);
@@ -206,13 +210,13 @@ istft_masked_kernel(IstftParams p) {
                 const int k = lane + 32 * r, kp = 1024 - k;
                 float2 xk = row[k];
                 float2 xp = row[kp];
-                if (p.mode == 1) {
+                if (MODE == 1) {
                     if (t_in && k >= f0 && k < f1) xk = make_float2(p.occlusion_value, 0.f);
                     if (t_in && kp >= f0 && kp < f1) xp = make_float2(p.occlusion_value, 0.f);
-                } else if (p.mode == 3) {
+                } else if (MODE == 3) {
                     if (!(t_in && k >= f0 && k < f1)) xk = make_float2(0.f, 0.f);
                     if (!(t_in && kp >= f0 && kp < f1)) xp = make_float2(0.f, 0.f);
-                } else if (p.mode == 2) {
+                } else if (MODE == 2) {
                     const float gk = __ldg(&gain[k]), gp = __ldg(&gain[kp]);
                     xk.x *= gk; xk.y *= gk; xp.x *= gp; xp.y *= gp;
                 }
@@ -242,11 +246,13 @@ istft_masked_kernel(IstftParams p) {
             for (int i = 0; i < 8; ++i) {
                 const int slot = 2 * lane + 64 * i;
                 float2 o = make_float2(a0[i].x + v[i].x, a0[i].y + v[i].y);
-                float2 wss;
                 if (steady) {
-                    wss = *reinterpret_cast<const float2*>(&g_wss512[slot]);
+                    // steady state (all four overlapping frames exist): the envelope is the 512-periodic table; multiply by
+                    // its reciprocal (rounded once from double) instead of dividing
+                    const float2 rw = *reinterpret_cast<const float2*>(&g_rwss512[slot]);
+                    o.x *= rw.x; o.y *= rw.y;
                 } else {
-                    wss = make_float2(0.f, 0.f);
+                    float2 wss = make_float2(0.f, 0.f);
                     for (int j = 0; j < 4; ++j) {
                         const int tf = t - j;
                         if (tf >= 0 && tf < p.n_frames) {
@@ -254,9 +260,9 @@ istft_masked_kernel(IstftParams p) {
                             wss.x += w.x * w.x; wss.y += w.y * w.y;
                         }
                     }
+                    if (wss.x > 1.17549435e-38f) o.x /= wss.x;
+                    if (wss.y > 1.17549435e-38f) o.y /= wss.y;
                 }
-                if (wss.x > 1.17549435e-38f) o.x /= wss.x;
-                if (wss.y > 1.17549435e-38f) o.y /= wss.y;
                 if (n_base + slot < p.out_len) {
                     *reinterpret_cast<float2*>(yout + n_base + slot) = o;
                     sq += o.x * o.x + o.y * o.y;
@@ -639,7 +645,13 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     B200X_TRY(ensure_tables(s));
     static bool cfg = false;
-    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM)); cfg = true; }
+    if (!cfg) {
+        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
+        cfg = true;
+    }
     IstftParams p;
     p.S = reinterpret_cast<const float2*>(d_spec); p.stride = spec_stride; p.n_frames = n_frames;
     p.out_len = static_cast<long long>(HOP) * (n_frames - 1); p.out_stride = y_stride; p.y = d_y;
@@ -653,7 +665,12 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
     p.hops_per_strip = (static_cast<long long>(copies) * hops >= 30000) ? 29 : 13;
     const int strips = ceil_div(hops, p.hops_per_strip);
     dim3 grid(ceil_div(strips, DSP_WARPS), copies);
-    istft_masked_kernel<<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p);
+    switch (mode) {
+        case 0: istft_masked_kernel<0><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
+        case 1: istft_masked_kernel<1><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
+        case 2: istft_masked_kernel<2><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
+        default: istft_masked_kernel<3><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
+    }
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }

@@ -17,6 +17,7 @@ constexpr int FFT_TILE = 32 * 33;      // float2 elements of the per-warp transp
 __device__ float2 g_tw2048[2048];
 __device__ float g_hann[2048];
 __device__ float g_wss512[512];
+__device__ float g_rwss512[512];     // 1 / g_wss512
 
 __device__ __forceinline__ constexpr int brev5(int i) {
     return ((i & 1) << 4) | ((i & 2) << 2) | (i & 4) | ((i & 8) >> 2) | ((i & 16) >> 4);

@@ -65,6 +65,23 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
         : "memory");
     return ok != 0;
 }
+// Non-suspending wait (mbarrier.test_wait in a tight loop): the waiter reacts within a few cycles of the phase flip instead
+// of after try_wait's hardware wake-up; for single-thread roles whose reaction time sits on the critical path.
+__device__ __forceinline__ void mbar_spin_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 28)) __trap();
+    }
+}
 // Bounded wait: a protocol bug traps (-> launch failure reported to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
