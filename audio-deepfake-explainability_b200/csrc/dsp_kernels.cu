@@ -9,6 +9,7 @@
 //   * mel_resize_kernel ..... normalise ((x-mean)/(std+eps)), bilinear resize along time, bf16, written in both operand
 //                             layouts of the tokenizer GEMMs ([time][freq] and [freq][time])
 // All FFTs are warp-level (fft.cuh); HBM/L2 traffic is coalesced float2 / float4.
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -26,6 +27,7 @@ constexpr int DSP_WARPS = 4;                    // warps per CTA for the FFT ker
 constexpr int DSP_THREADS = DSP_WARPS * 32;
 constexpr int DSP_SMEM = (DSP_WARPS * FFT_TILE + FFT_TWIDDLE) * 8;
 constexpr int ISTFT_ROW = 1026;                 // float2 elements copied per spectrogram row (1025 bins + 1: 16-byte multiple)
+constexpr int MEL_SEGS_PER_LANE = 5;            // ceil((128 + 1) / 32)
 constexpr int MEL_SMEM = DSP_SMEM + DSP_WARPS * 2048 * 4 + DSP_WARPS * 8;   // + one staged 2048-sample frame and one mbarrier per warp
 constexpr int ISTFT_SMEM = DSP_SMEM + DSP_WARPS * 2 * ISTFT_ROW * 8 + DSP_WARPS * 2 * 8;
 
@@ -295,10 +297,11 @@ struct MelParams {
     long long rms_count;
     int n_frames;
     int n_mels;                // <= 128, multiple of 32
-    const int* fb_start;       // [n_mels] first bin with a non-zero weight
-    const int* fb_count;       // [n_mels]
-    const int* fb_offset;      // [n_mels] offset into fb_weights
-    const float* fb_weights;
+    // triangular filterbank by SEGMENTS between consecutive centre frequencies: a bin of segment j feeds filter j with its
+    // rising weight (.x) and filter j - 1 with its falling weight (.y), so mel[m] = U[m] + D[m + 1] with two sums per segment
+    const int* seg_start;      // [n_mels + 2] first bin of segment j (segment n_mels + 1 = end sentinel)
+    const float2* seg_weights; // [NBIN] (rising, falling) weight of every bin
+    const int* lane_segments;  // [32][MEL_SEGS_PER_LANE] segments summed by each lane (balanced by width, -1 = none)
     float amin;
     float* db;                 // [copies][db_frames][n_mels]; row (t - ma) when frame_range is given
     float* cta_max;            // [copies][gridDim.x]
@@ -407,11 +410,29 @@ mel_db_kernel(MelParams p) {
         if (lane == 0) pw[1024] = xn.x * xn.x;
         __syncwarp();
         float* out = p.db + (static_cast<long long>(copy) * p.db_frames + (t - f_lo)) * p.n_mels;
+        // filterbank: every lane sums its (width-balanced) segments, two accumulators per segment; the per-filter serial
+        // loop this replaces made the lane with the widest filters run ~80 dependent load + FMA steps per frame
+        float* segU = pw + 1056;
+        float* segD = segU + 160;
+#pragma unroll
+        for (int sidx = 0; sidx < MEL_SEGS_PER_LANE; ++sidx) {
+            const int j = __ldg(&p.lane_segments[lane * MEL_SEGS_PER_LANE + sidx]);
+            if (j < 0) continue;
+            const int kb = __ldg(&p.seg_start[j]), ke = __ldg(&p.seg_start[j + 1]);
+            float au = 0.f, ad = 0.f;
+#pragma unroll 4
+            for (int k = kb; k < ke; ++k) {
+                const float2 w = __ldg(&p.seg_weights[k]);
+                const float x = pw[k];
+                au = fmaf(w.x, x, au);
+                ad = fmaf(w.y, x, ad);
+            }
+            segU[j] = au;
+            segD[j] = ad;
+        }
+        __syncwarp();
         for (int f = lane; f < p.n_mels; f += 32) {
-            const int st = __ldg(&p.fb_start[f]), cnt = __ldg(&p.fb_count[f]);
-            const float* w = p.fb_weights + __ldg(&p.fb_offset[f]);
-            float acc = 0.f;
-            for (int i = 0; i < cnt; ++i) acc = fmaf(__ldg(&w[i]), pw[st + i], acc);
+            const float acc = segU[f] + segD[f + 1];
             const float d = 10.0f * log10f(fmaxf(acc, p.amin));
             out[f] = d;
             vmax = fmaxf(vmax, d);
@@ -679,12 +700,14 @@ namespace b200x {
 // HTK mel filterbank, torchaudio.functional.melscale_fbanks(norm=None, mel_scale='htk') restated; sparse rows.
 struct MelBank {
     int n_mels = 0;
-    int *d_start = nullptr, *d_count = nullptr, *d_offset = nullptr;
-    float* d_weights = nullptr;
+    int *d_seg_start = nullptr, *d_lane_segments = nullptr;
+    float2* d_seg_weights = nullptr;
 };
 static MelBank g_bank;
 static double g_bank_key[4] = {0, 0, 0, 0};
 
+// HTK triangular filters, unnormalised (torchaudio melscale_fbanks(norm=None, mel_scale="htk")): w[f][k] =
+// max(0, min(rising, falling)) in double, rounded to float.  Stored by segment (see MelParams).
 static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_max) {
     if (g_bank.n_mels == n_mels && g_bank_key[0] == sample_rate && g_bank_key[1] == f_min && g_bank_key[2] == f_max)
         return B200X_OK;
@@ -694,33 +717,49 @@ static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_ma
         const double m = m_min + (m_max - m_min) * i / (n_mels + 1);
         f_pts[i] = 700.0 * (std::pow(10.0, m / 2595.0) - 1.0);
     }
-    std::vector<int> start(n_mels), count(n_mels), offset(n_mels);
-    std::vector<float> weights;
-    for (int f = 0; f < n_mels; ++f) {
-        int first = -1, last = -1;
-        std::vector<float> w(NBIN, 0.f);
-        for (int k = 0; k < NBIN; ++k) {
-            const double freq = static_cast<double>(k) * (sample_rate / 2) / (NBIN - 1);
-            const double down = (freq - f_pts[f]) / (f_pts[f + 1] - f_pts[f]);
-            const double up = (f_pts[f + 2] - freq) / (f_pts[f + 2] - f_pts[f + 1]);
-            const double v = std::max(0.0, std::min(down, up));
-            if (v > 0.0) { if (first < 0) first = k; last = k; w[k] = static_cast<float>(v); }
-        }
-        start[f] = first < 0 ? 0 : first;
-        count[f] = first < 0 ? 0 : last - first + 1;
-        offset[f] = static_cast<int>(weights.size());
-        for (int k = 0; k < count[f]; ++k) weights.push_back(w[start[f] + k]);
+    auto weight = [&](int f, int k) -> float {
+        if (f < 0 || f >= n_mels) return 0.f;
+        const double freq = static_cast<double>(k) * (sample_rate / 2) / (NBIN - 1);
+        const double rising = (freq - f_pts[f]) / (f_pts[f + 1] - f_pts[f]);
+        const double falling = (f_pts[f + 2] - freq) / (f_pts[f + 2] - f_pts[f + 1]);
+        return static_cast<float>(std::max(0.0, std::min(rising, falling)));
+    };
+    // segment of bin k: the j with f_pts[j] < freq <= f_pts[j + 1] (clamped to [0, n_mels]); it feeds filters j and j - 1
+    const int n_seg = n_mels + 1;
+    std::vector<int> seg_of(NBIN), seg_start(n_seg + 1, NBIN);
+    std::vector<float2> w(NBIN);
+    for (int k = 0; k < NBIN; ++k) {
+        const double freq = static_cast<double>(k) * (sample_rate / 2) / (NBIN - 1);
+        int j = 0;
+        while (j < n_mels && freq > f_pts[j + 1]) ++j;
+        seg_of[k] = j;
+        w[k] = make_float2(weight(j, k), weight(j - 1, k));
+        // every other filter must be silent at this bin, or the two-filter decomposition would drop weight
+        for (int f = 0; f < n_mels; ++f)
+            if (f != j && f != j - 1 && weight(f, k) != 0.f)
+                return set_error(B200X_ERR_INVALID, "mel bank: bin %d feeds filter %d outside its segment %d", k, f, j);
     }
-    if (weights.empty()) weights.push_back(0.f);
-    if (g_bank.d_start) { cudaFree(g_bank.d_start); cudaFree(g_bank.d_count); cudaFree(g_bank.d_offset); cudaFree(g_bank.d_weights); }
-    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_start, n_mels * sizeof(int)));
-    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_count, n_mels * sizeof(int)));
-    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_offset, n_mels * sizeof(int)));
-    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_weights, weights.size() * sizeof(float)));
-    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_start, start.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
-    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_count, count.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
-    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_offset, offset.data(), n_mels * sizeof(int), cudaMemcpyHostToDevice));
-    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (int k = NBIN - 1; k >= 0; --k) seg_start[seg_of[k]] = k;
+    for (int j = n_seg - 1; j >= 0; --j) seg_start[j] = std::min(seg_start[j], seg_start[j + 1]);   // empty segments
+    // longest-first greedy assignment of segments to lanes
+    std::vector<int> order(n_seg), load(32, 0), used(32, 0), lane_segs(32 * MEL_SEGS_PER_LANE, -1);
+    for (int j = 0; j < n_seg; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seg_start[a + 1] - seg_start[a] > seg_start[b + 1] - seg_start[b]; });
+    for (int j : order) {
+        int best = -1;
+        for (int l = 0; l < 32; ++l)
+            if (used[l] < MEL_SEGS_PER_LANE && (best < 0 || load[l] < load[best])) best = l;
+        if (best < 0) return set_error(B200X_ERR_INVALID, "mel bank: %d segments do not fit 32 x %d lane slots", n_seg, MEL_SEGS_PER_LANE);
+        lane_segs[best * MEL_SEGS_PER_LANE + used[best]++] = j;
+        load[best] += seg_start[j + 1] - seg_start[j] + 2;
+    }
+    if (g_bank.d_seg_start) { cudaFree(g_bank.d_seg_start); cudaFree(g_bank.d_lane_segments); cudaFree(g_bank.d_seg_weights); }
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_seg_start, seg_start.size() * sizeof(int)));
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_lane_segments, lane_segs.size() * sizeof(int)));
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_seg_weights, NBIN * sizeof(float2)));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_seg_start, seg_start.data(), seg_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_lane_segments, lane_segs.data(), lane_segs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_seg_weights, w.data(), NBIN * sizeof(float2), cudaMemcpyHostToDevice));
     g_bank.n_mels = n_mels;
     g_bank_key[0] = sample_rate; g_bank_key[1] = f_min; g_bank_key[2] = f_max;
     return B200X_OK;
@@ -743,7 +782,7 @@ extern "C" int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_sample
     MelParams p;
     p.y = d_y; p.y_stride = y_stride; p.n_samples = n_samples; p.sumsq = d_sumsq; p.ref_rms = ref_rms; p.rms_count = rms_count;
     p.n_frames = 1 + static_cast<int>(n_samples / HOP); p.n_mels = n_mels;
-    p.fb_start = g_bank.d_start; p.fb_count = g_bank.d_count; p.fb_offset = g_bank.d_offset; p.fb_weights = g_bank.d_weights;
+    p.seg_start = g_bank.d_seg_start; p.seg_weights = g_bank.d_seg_weights; p.lane_segments = g_bank.d_lane_segments;
     p.amin = static_cast<float>(amin); p.db = d_db; p.cta_max = d_cta_max; p.frames_per_cta = b200x_mel_frames_per_cta();
     p.db_frames = db_frames; p.frame_range = d_frame_range;
     const int span = d_frame_range ? std::min(p.n_frames, std::max(1, max_range_frames)) : p.n_frames;
