@@ -173,3 +173,22 @@ def test_stem_mask_sweep_matches_oracle(predictor, oracle_predictor):
     assert got.shape == want.shape == (12, 2)
     assert np.abs(got - want).max() < TOL
     assert np.allclose(got.sum(1), 1.0)
+
+
+def test_lime_explain_stems_matches_oracle(predictor, oracle_predictor):
+    from audio_deepfake_explainability_b200 import lime_explainer as le
+    stems = np.stack(list(synth.synth_stems("SUNO_PRO", 2, SR, 6.0).values())[:4]).astype(np.float32)
+    exp = le.explain_stems(stems, predictor, num_samples=60, random_state=0)
+    full = le.explain_stems(stems, predictor, num_samples=60, random_state=0, deduplicate=False)
+    assert np.array_equal(exp.masks, le.lime_masks(60, 4, 0))
+    assert np.array_equal(exp.probabilities, full.probabilities)            # de-duplicating the <= 16 distinct masks changes no bit
+    assert exp.local_exp == full.local_exp
+    uniq = np.unique(exp.masks, axis=0)
+    want = {tuple(m): p for m, p in zip(uniq.tolist(), loops.stem_mask_probs(stems, uniq, oracle_predictor, SR))}
+    ref_probs = np.array([want[tuple(m)] for m in exp.masks.tolist()])
+    assert np.abs(exp.probabilities - ref_probs).max() < TOL
+    ref = le.fit_lime(exp.masks, ref_probs)
+    assert exp.top_label == ref.top_label
+    assert np.abs(np.array([exp.by_feature[n] for n in le.COMPONENT_NAMES_4STEMS])
+                  - np.array([ref.by_feature[n] for n in le.COMPONENT_NAMES_4STEMS])).max() < TOL
+    assert le.predict_fn_unified(stems.sum(0), predictor).shape == (1, 2)
