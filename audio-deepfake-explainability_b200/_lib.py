@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200x_head": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, VP, VP, C.c_float, C.c_int, VP, C.c_float, VP, VP, VP, VP]),
     "b200x_delta": (C.c_int, [VP, C.c_float, C.c_int, VP, VP]),
     "b200x_saliency_reduce": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, VP, VP]),
+    "b200x_rise_map": (C.c_int, [VP, C.c_int, C.c_uint32, C.c_double, C.c_int, C.c_int, VP, VP]),
     "b200x_band_map": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, VP, VP]),
     "b200x_rank": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),
     "b200x_engine_create": (C.c_int, [C.POINTER(ModelConfig), C.c_int, C.c_int64, C.POINTER(VP)]),
@@ -72,6 +73,9 @@ SIGNATURES = {
     "b200x_engine_occluded_audio": (C.c_int, [VP, VP, C.c_int, C.c_float, VP]),
     "b200x_engine_band_audio": (C.c_int, [VP, VP, C.c_int, VP]),
     "b200x_engine_saliency_map": (C.c_int, [VP, VP, VP, C.c_int, VP]),
+    "b200x_engine_rise_sweep": (C.c_int, [VP, C.c_int, C.c_int, C.c_uint32, C.c_double, C.c_int, VP]),
+    "b200x_engine_rise_audio": (C.c_int, [VP, C.c_int, C.c_int, C.c_uint32, C.c_double, VP]),
+    "b200x_engine_rise_map": (C.c_int, [VP, VP, C.c_int, C.c_uint32, C.c_double, VP]),
     "b200x_engine_band_map": (C.c_int, [VP, VP, VP, C.c_int, VP]),
     "b200x_engine_rank": (C.c_int, [VP, VP, C.c_int, C.c_int, VP]),
     "b200x_engine_debug_buffer": (C.c_int, [VP, C.c_char_p, C.POINTER(VP), C.POINTER(C.c_int64)]),

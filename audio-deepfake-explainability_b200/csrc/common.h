@@ -42,4 +42,23 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// RISE keep mask (src/spectrogram_explainability.py:768: an i.i.d. Bernoulli(p) bit per spectrogram cell and mask; the
+// reference draws it from the UNSEEDED numpy global RNG, so the bit generator here is the builder's: a counter-based hash
+// of (seed, mask index, cell) that the iSTFT load stage, the map reduction and the CPU oracle all evaluate identically).
+__host__ __device__ inline uint32_t hash_lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ inline uint32_t rise_mask_key(uint32_t seed, uint32_t mask_index) {
+    return hash_lowbias32(seed * 0x9E3779B9U + mask_index * 0x85EBCA6BU + 0x165667B1U);
+}
+// cell = frame * 1025 + bin; kept iff the 32-bit uniform is below floor(p * 2^32)
+__host__ __device__ inline bool rise_keep(uint32_t key, uint32_t cell, uint32_t threshold) {
+    return hash_lowbias32(key ^ (cell * 0xC2B2AE35U)) < threshold;
+}
+inline uint32_t rise_threshold(double keep_probability) {
+    const double v = keep_probability * 4294967296.0;
+    return v >= 4294967295.0 ? 4294967295U : (v <= 0.0 ? 0U : static_cast<uint32_t>(v));
+}
+
 }  // namespace b200x

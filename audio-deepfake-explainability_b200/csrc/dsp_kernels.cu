@@ -166,7 +166,7 @@ istft_masked_kernel(IstftParams p) {
     const int hp_b = min(hp_a + p.hops_per_strip, h_hi + 1);
     if (hp_a >= hp_b) return;
     int t0 = 0, t1 = 0, f0 = 0, f1 = 0;
-    if (MODE == 1 || MODE == 3) {
+    if (MODE == 1 || MODE == 3 || MODE == 4) {
         const int4 w = *reinterpret_cast<const int4*>(p.windows + 4 * copy);
         t0 = w.x; t1 = w.y; f0 = w.z; f1 = w.w;
     }
@@ -218,6 +218,11 @@ istft_masked_kernel(IstftParams p) {
                 } else if (MODE == 3) {
                     if (!(t_in && k >= f0 && k < f1)) xk = make_float2(0.f, 0.f);
                     if (!(t_in && kp >= f0 && kp < f1)) xp = make_float2(0.f, 0.f);
+                } else if (MODE == 4) {                  // RISE: windows row = (seed, mask index, keep threshold, -)
+                    const uint32_t key = rise_mask_key(static_cast<uint32_t>(t0), static_cast<uint32_t>(t1));
+                    const uint32_t cell = static_cast<uint32_t>(t) * NBIN;
+                    if (!rise_keep(key, cell + k, static_cast<uint32_t>(f0))) xk = make_float2(0.f, 0.f);
+                    if (!rise_keep(key, cell + kp, static_cast<uint32_t>(f0))) xp = make_float2(0.f, 0.f);
                 } else if (MODE == 2) {
                     const float gk = __ldg(&gain[k]), gp = __ldg(&gain[kp]);
                     xk.x *= gk; xk.y *= gk; xp.x *= gp; xp.y *= gp;
@@ -657,8 +662,8 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
                                   const int32_t* d_windows, float occlusion_value, const float* d_gains, float* d_y,
                                   int64_t y_stride, double* d_sumsq, const int32_t* d_frame_range, int max_range_frames,
                                   void* stream) {
-    B200X_REQUIRE(mode >= 0 && mode <= 3, "istft: bad mode %d", mode);
-    B200X_REQUIRE((mode != 1 && mode != 3) || d_windows != nullptr, "istft: windows missing");
+    B200X_REQUIRE(mode >= 0 && mode <= 4, "istft: bad mode %d", mode);
+    B200X_REQUIRE((mode != 1 && mode != 3 && mode != 4) || d_windows != nullptr, "istft: windows missing");
     B200X_REQUIRE(mode != 2 || d_gains != nullptr, "istft: gains missing");
     B200X_REQUIRE(n_frames >= 2 && copies > 0, "istft: bad sizes");
     B200X_REQUIRE(spec_stride >= ISTFT_ROW && spec_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(d_spec) & 15) == 0,
@@ -671,6 +676,7 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
         B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
         B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
         B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
         cfg = true;
     }
     IstftParams p;
@@ -690,7 +696,8 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
         case 0: istft_masked_kernel<0><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
         case 1: istft_masked_kernel<1><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
         case 2: istft_masked_kernel<2><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
-        default: istft_masked_kernel<3><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
+        case 3: istft_masked_kernel<3><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
+        default: istft_masked_kernel<4><<<grid, DSP_THREADS, ISTFT_SMEM, s>>>(p); break;
     }
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;

@@ -741,6 +741,62 @@ extern "C" int b200x_engine_band_audio(b200x_engine* e, const float* gains, int 
     return audio_out(e, B200X_MASK_BAND_GAIN, nullptr, gains, n, 0.f, audio_host, 0, nullptr);
 }
 
+namespace {
+// RISE rows for the iSTFT load stage: (seed, mask index, keep threshold, 0) per perturbed copy
+std::vector<int32_t> rise_rows(int first_mask, int n, uint32_t seed, double keep_probability) {
+    std::vector<int32_t> rows(static_cast<size_t>(n) * 4);
+    const uint32_t thr = rise_threshold(keep_probability);
+    for (int i = 0; i < n; ++i) {
+        rows[4 * i] = static_cast<int32_t>(seed);
+        rows[4 * i + 1] = first_mask + i;
+        rows[4 * i + 2] = static_cast<int32_t>(thr);
+        rows[4 * i + 3] = 0;
+    }
+    return rows;
+}
+}  // namespace
+
+extern "C" int b200x_engine_rise_sweep(b200x_engine* e, int first_mask, int n, uint32_t seed, double keep_probability,
+                                       int on_device, float* prob) {
+    B200X_TRY(check_ready(e, true));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(prob && n > 0 && first_mask >= 0, "rise_sweep: bad argument");
+    B200X_REQUIRE(keep_probability > 0.0 && keep_probability <= 1.0, "rise_sweep: keep probability %g outside (0, 1]", keep_probability);
+    B200X_TRY(ensure_prob(e, n));
+    const std::vector<int32_t> rows = rise_rows(first_mask, n, seed, keep_probability);
+    B200X_TRY(ensure_grow(e->windows, rows.size() * sizeof(int32_t)));
+    B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));          // rows is a stack-lifetime staging buffer
+    B200X_TRY(sweep(e, B200X_MASK_RANDOM_KEEP, n, e->windows.as<int32_t>(), 0.f, nullptr, false, e->prob.as<float>()));
+    B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_rise_audio(b200x_engine* e, int first_mask, int n, uint32_t seed, double keep_probability,
+                                       float* audio_host) {
+    B200X_TRY(check_ready(e, true));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(audio_host && n > 0 && first_mask >= 0, "rise_audio: bad argument");
+    const std::vector<int32_t> rows = rise_rows(first_mask, n, seed, keep_probability);
+    return audio_out(e, B200X_MASK_RANDOM_KEEP, rows.data(), nullptr, n, 0.f, audio_host, 0, nullptr);
+}
+
+extern "C" int b200x_engine_rise_map(b200x_engine* e, const double* pred, int n, uint32_t seed, double keep_probability,
+                                     double* map_host) {
+    B200X_TRY(check_ready(e, true));
+    B200X_REQUIRE(map_host && n >= 0 && (n == 0 || pred), "rise_map: bad argument");
+    const size_t cells = static_cast<size_t>(b200x_engine::n_freq) * e->n_time;
+    B200X_TRY(ensure_grow(e->map, cells * sizeof(double)));
+    B200X_TRY(ensure_grow(e->delta, static_cast<size_t>(std::max(n, 1)) * sizeof(double)));
+    if (n > 0) B200X_CUDA_TRY(cudaMemcpyAsync(e->delta.p, pred, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    B200X_TRY(b200x_rise_map(e->delta.as<double>(), n, seed, keep_probability, b200x_engine::n_freq, e->n_time, e->map.as<double>(), e->stream));
+    e->launches += 1;
+    B200X_CUDA_TRY(cudaMemcpyAsync(map_host, e->map.p, cells * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
 extern "C" int b200x_engine_saliency_map(b200x_engine* e, const int32_t* windows, const double* delta, int n,
                                          double* map_host) {
     B200X_TRY(check_ready(e, true));

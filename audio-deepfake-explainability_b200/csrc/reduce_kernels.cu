@@ -245,6 +245,39 @@ extern "C" int b200x_delta(const float* d_prob, float baseline, int n, double* d
     return B200X_OK;
 }
 
+namespace b200x {
+// RISE accumulation (src/spectrogram_explainability.py:783, :798): map[f][t] = sum_i keep_i(f, t) * pred[i], float64 in mask
+// order (adding the reference's 0.0 * pred terms would not change a bit), then / (n_masks * p + 1e-8).  The keep bits are
+// re-derived from the hash, so no mask is ever stored.
+__global__ void __launch_bounds__(256)
+rise_map_kernel(const double* __restrict__ pred, int n_masks, uint32_t seed, uint32_t threshold, double denom, int n_freq,
+                int n_time, double* __restrict__ map) {
+    extern __shared__ uint32_t s_keys[];
+    for (int i = threadIdx.x; i < n_masks; i += blockDim.x) s_keys[i] = rise_mask_key(seed, static_cast<uint32_t>(i));
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (t >= n_time) return;
+    const uint32_t cell = static_cast<uint32_t>(t) * static_cast<uint32_t>(n_freq) + static_cast<uint32_t>(f);
+    double acc = 0.0;
+    for (int i = 0; i < n_masks; ++i)
+        if (rise_keep(s_keys[i], cell, threshold)) acc += pred[i];
+    map[static_cast<long long>(f) * n_time + t] = acc / denom;
+}
+}  // namespace b200x
+
+extern "C" int b200x_rise_map(const double* d_pred, int n_masks, uint32_t seed, double keep_probability, int n_freq, int n_time,
+                              double* d_map, void* stream) {
+    B200X_REQUIRE(n_freq > 0 && n_time > 0 && n_masks >= 0 && n_masks <= 12000, "rise_map: bad sizes");
+    B200X_REQUIRE(n_freq == 1025, "rise_map: the cell index is frame * 1025 + bin (got n_freq=%d)", n_freq);
+    dim3 grid(ceil_div(n_time, 256), n_freq);
+    const double denom = static_cast<double>(n_masks) * keep_probability + 1e-8;
+    rise_map_kernel<<<grid, 256, static_cast<size_t>(n_masks > 0 ? n_masks : 1) * sizeof(uint32_t), static_cast<cudaStream_t>(stream)>>>(
+        d_pred, n_masks, seed, rise_threshold(keep_probability), denom, n_freq, n_time, d_map);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
 extern "C" int b200x_saliency_reduce(const int32_t* d_windows, const double* d_delta, int n_windows, int n_freq,
                                      int n_time, double* d_map, void* stream) {
     B200X_REQUIRE(n_freq > 0 && n_time > 0 && n_windows >= 0, "saliency: bad sizes");

@@ -165,6 +165,29 @@ class Engine:
         _lib.check(self.lib.b200x_engine_band_audio(self._h, _ptr(g), g.shape[0], _ptr(out)), "band_audio")
         return out
 
+    # ------------------------------------------------------------------ RISE (random keep masks generated on the device)
+    def rise_sweep(self, n_masks: int, seed: int, keep_probability: float, first_mask: int = 0) -> np.ndarray:
+        prob = np.empty(int(n_masks), np.float32)
+        _lib.check(self.lib.b200x_engine_rise_sweep(self._h, int(first_mask), int(n_masks), int(seed) & 0xFFFFFFFF,
+                                                    float(keep_probability), 0, _ptr(prob)), "rise_sweep")
+        return prob
+
+    def rise_audio(self, n_masks: int, seed: int, keep_probability: float, first_mask: int = 0) -> np.ndarray:
+        _, t = self.track_shape()
+        out = np.empty((int(n_masks), self.cfg.hop_length * (t - 1)), np.float32)
+        _lib.check(self.lib.b200x_engine_rise_audio(self._h, int(first_mask), int(n_masks), int(seed) & 0xFFFFFFFF,
+                                                    float(keep_probability), _ptr(out)), "rise_audio")
+        return out
+
+    def rise_map(self, predictions: np.ndarray, seed: int, keep_probability: float) -> np.ndarray:
+        """``sum_i mask_i * pred_i / (n_masks * p + 1e-8)`` (float64 ``[n_freq, n_time]``, before the min-max scaling)."""
+        pr = np.ascontiguousarray(np.asarray(predictions, dtype=np.float64))
+        f, t = self.track_shape()
+        out = np.empty((f, t), np.float64)
+        _lib.check(self.lib.b200x_engine_rise_map(self._h, _ptr(pr), pr.shape[0], int(seed) & 0xFFFFFFFF, float(keep_probability),
+                                                  _ptr(out)), "rise_map")
+        return out
+
     # ------------------------------------------------------------------ reductions
     def saliency_map(self, windows: np.ndarray, delta: np.ndarray) -> np.ndarray:
         w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)

@@ -29,6 +29,14 @@ class OcclusionResult(NamedTuple):
     patch_importances: Optional[list]
 
 
+class RiseResult(NamedTuple):
+    importance_map: Optional[np.ndarray]
+    spectrogram_db: np.ndarray
+    baseline_pred: float
+    y: np.ndarray
+    S: np.ndarray
+
+
 def amplitude_to_db_refmax(S: np.ndarray) -> np.ndarray:
     """``librosa.amplitude_to_db(np.abs(S), ref=np.max)`` (visualisation only, :387)."""
     mag = np.abs(S).astype(np.float32)
@@ -89,7 +97,7 @@ class SpectrogramExplainability:
                  use_original_audio: bool = True, patch_time_frames: int = 2048, stride_time_frames: int = 2048,
                  patch_freq_percent: float = 25.0, stride_freq_percent: float = 25.0, n_masks: int = 500,
                  mask_probability: float = 0.5, checkpoint_dir=None, highlight_percent: float = 20.0,
-                 abs_threshold: float = 0.0):
+                 abs_threshold: float = 0.0, rise_seed: int = 0):
         if not isinstance(predictor, B200Predictor):
             raise TypeError("the B200 occlusion sweep needs a B200Predictor (the classifier runs inside the sweep); "
                             f"got {type(predictor).__name__}")
@@ -107,17 +115,18 @@ class SpectrogramExplainability:
         self.patch_freq_percent, self.stride_freq_percent = patch_freq_percent, stride_freq_percent
         self.use_original_audio = use_original_audio
         self.n_masks, self.mask_probability = n_masks, mask_probability
+        self.rise_seed = rise_seed          # the reference draws RISE masks from the unseeded numpy global RNG (:768)
         self.highlight_percent, self.abs_threshold = highlight_percent, abs_threshold
         self.checkpoint = SpectrogramCheckpoint(checkpoint_dir) if checkpoint_dir else None
 
     # -- guards for the variants that have no reference parity ----------------
-    def _require_stft_occlusion(self) -> None:
+    def _require_stft_occlusion(self, method: str = "occlusion") -> None:
         if self.spec_type != "stft":
             raise NotImplementedError("spec_type='mel' inverts through Griffin-Lim with unseeded random phase in the "
                                       "reference (:394-402) and is not part of the parity path; use spec_type='stft'")
-        if self.method != "occlusion":
-            raise NotImplementedError("method='rise' uses unseeded random masks in the reference (:768); only "
-                                      "method='occlusion' is built")
+        if self.method != method:
+            raise NotImplementedError(f"this explainer was built with method={self.method!r}; "
+                                      f"{'_compute_rise_map' if self.method == 'rise' else '_compute_occlusion_map'} is its entry point")
         if (self.n_fft, self.hop_length, self.win_length) != (2048, 512, 2048):
             raise NotImplementedError("the CUDA STFT/iSTFT kernels are built for n_fft=2048, hop=512, win=2048")
 
@@ -126,7 +135,7 @@ class SpectrogramExplainability:
 
     def _compute_spectrogram(self, y: np.ndarray):
         """(S, S_db) with S = complex64 ``[1025, 1 + len(y)//512]`` computed on the GPU (librosa.stft semantics)."""
-        self._require_stft_occlusion()
+        self._require_stft_occlusion(self.method)
         self.predictor.engine.set_track(y)
         S = self.predictor.engine.spectrogram()
         return S, amplitude_to_db_refmax(S)
@@ -162,6 +171,38 @@ class SpectrogramExplainability:
         if verbose:
             print(f"    Completed | Mean importance: {importance_map.mean():.4f}, Max: {importance_map.max():.4f}")
         return OcclusionResult(importance_map, S_db, baseline_pred, y, S, patch_importances)
+
+    # -- RISE (:722-806) -------------------------------------------------------------------------------
+    def rise_map_from_wave(self, y: np.ndarray, baseline_threshold: float = 0.3, verbose: bool = True) -> RiseResult:
+        """``n_masks`` i.i.d. Bernoulli(``mask_probability``) keep masks over the STFT, each -> iSTFT -> prediction;
+        ``map = sum_i mask_i * pred_i / (n_masks * p + 1e-8)`` scaled to [0, 1].  The masks never exist in memory: the iSTFT
+        load stage and the map reduction both evaluate the same counter-based hash of (``rise_seed``, mask, cell).  The
+        reference draws them from numpy's unseeded global RNG, so individual runs are not comparable bit for bit even
+        reference-vs-reference; parity is against ``oracle/loops.py::rise_map`` with the same hash."""
+        self._require_stft_occlusion("rise")
+        eng = self.predictor.engine
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float32))
+        eng.set_track(y)
+        S = eng.spectrogram()
+        S_db = amplitude_to_db_refmax(S)
+        baseline_pred = float(eng.predict(y))
+        if verbose:
+            print(f"    Baseline prediction: {baseline_pred:.4f}")
+        if baseline_pred < baseline_threshold:
+            return RiseResult(None, S_db, baseline_pred, y, S)
+        rank, world = dist.world()
+        lo, hi = grid.shard_range(self.n_masks, rank, world)            # masks are independent: shard them like windows
+        local = eng.rise_sweep(hi - lo, self.rise_seed, self.mask_probability, first_mask=lo) if hi > lo else np.zeros(0, np.float32)
+        preds = dist.gather_shards(local, self.n_masks)
+        importance_map = eng.rise_map(np.array([float(p) for p in preds], dtype=np.float64), self.rise_seed, self.mask_probability)
+        importance_map = (importance_map - importance_map.min()) / (importance_map.max() - importance_map.min() + 1e-8)
+        if verbose:
+            print(f"    Completed | Mean importance: {importance_map.mean():.4f}, Max: {importance_map.max():.4f}")
+        return RiseResult(importance_map, S_db, baseline_pred, y, S)
+
+    def _compute_rise_map(self, audio_path: str, baseline_threshold: float = 0.3, verbose: bool = True) -> RiseResult:
+        y, _ = load_audio(audio_path, sr=self.sr, duration=self.duration, mono=True)
+        return self.rise_map_from_wave(y, baseline_threshold, verbose)
 
     def _compute_occlusion_map(self, audio_path: str, occlusion_value: float = 0.0, baseline_threshold: float = 0.3,
                                verbose: bool = True) -> OcclusionResult:

@@ -37,6 +37,9 @@ extern "C" {
 #define B200X_MASK_OCCLUDE 1   /* S[f0:f1, t0:t1] = value          (spectrogram_explainability.py:670-671) */
 #define B200X_MASK_BAND_GAIN 2 /* S *= gain[f]                     (dsp_band_ops.py:576-579)               */
 #define B200X_MASK_KEEP_ONLY 3 /* zeros except S[f0:f1, t0:t1]     (spectrogram_explainability.py:472-475) */
+#define B200X_MASK_RANDOM_KEEP 4 /* S *= Bernoulli(p) bit per cell (RISE, spectrogram_explainability.py:768-769); the row of
+                                  * d_windows is (seed, mask index, floor(p 2^32) as int32 bits, 0); the bit of cell
+                                  * (frame t, bin k) is hash(seed, mask, t * 1025 + k) < threshold (common.h: rise_keep) */
 
 const char* b200x_last_error(void);
 int b200x_version(void);
@@ -129,6 +132,11 @@ int b200x_delta(const float* d_prob, float baseline, int n, double* d_delta, voi
 int b200x_saliency_reduce(const int32_t* d_windows, const double* d_delta, int n_windows, int n_freq, int n_time,
                           double* d_map, void* stream);
 
+/* RISE: map[f][t] = sum_i keep_i(f, t) * pred[i] / (n_masks * p + 1e-8), float64 in mask order; the keep bits are re-derived
+ * from the hash of B200X_MASK_RANDOM_KEEP (src/spectrogram_explainability.py:783, :798; min-max scaling :801 is the caller's) */
+int b200x_rise_map(const double* d_pred, int n_masks, uint32_t seed, double keep_probability, int n_freq, int n_time,
+                   double* d_map, void* stream);
+
 /* FBP rows: map[rows[b][0]:rows[b][1], :] += delta[b]  (src/dsp_band_ops.py:652-653) */
 int b200x_band_map(const int32_t* d_band_rows, const double* d_delta, int n_bands, int n_freq, int n_time,
                    double* d_map, void* stream);
@@ -195,6 +203,12 @@ int b200x_engine_band_audio(b200x_engine* e, const float* gains, int n, float* a
 
 /* Reductions on host buffers (map is float64 [n_freq][n_time]). */
 int b200x_engine_saliency_map(b200x_engine* e, const int32_t* windows, const double* delta, int n, double* map_host);
+/* RISE (src/spectrogram_explainability.py:722-806): probabilities of masks first_mask .. first_mask + n - 1 of the track set
+ * with set_track (mask generated in the iSTFT load stage, never stored), their masked audio (tests), and the accumulated map */
+int b200x_engine_rise_sweep(b200x_engine* e, int first_mask, int n, uint32_t seed, double keep_probability, int on_device,
+                            float* prob);
+int b200x_engine_rise_audio(b200x_engine* e, int first_mask, int n, uint32_t seed, double keep_probability, float* audio_host);
+int b200x_engine_rise_map(b200x_engine* e, const double* pred, int n, uint32_t seed, double keep_probability, double* map_host);
 int b200x_engine_band_map(b200x_engine* e, const int32_t* band_rows, const double* delta, int n, double* map_host);
 int b200x_engine_rank(b200x_engine* e, const double* values, int n, int mode, int32_t* order_host);
 

@@ -220,3 +220,61 @@ def stem_mask_probs(stems: np.ndarray, masks: np.ndarray, predictor, sr: int) ->
         p = float(predictor.predict(x, sr))
         out[i] = (1.0 - p, p)
     return out
+
+
+# ------------------------------------------------------------------------------------------------- RISE (:722-806)
+def _lowbias32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint64)
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def rise_keep_mask(seed: int, mask_index: int, n_freq: int, n_time: int, keep_probability: float) -> np.ndarray:
+    """Keep mask ``[n_freq, n_time]`` (bool) of one RISE iteration.  The reference's ``np.random.rand(n_freq, n_time) >
+    1 - p`` (:768) uses the unseeded global RNG; the build defines the bits as a counter-based hash of (seed, mask, cell)
+    (csrc/common.h: rise_mask_key / rise_keep) - restated here in numpy so that the CPU loop sees the very same masks."""
+    m32 = np.uint64(0xFFFFFFFF)
+    key = _lowbias32(np.array([(np.uint64(seed & 0xFFFFFFFF) * np.uint64(0x9E3779B9) + np.uint64(mask_index) * np.uint64(0x85EBCA6B)
+                                + np.uint64(0x165667B1)) & m32]))[0]
+    t = np.arange(n_time, dtype=np.uint64)[None, :]
+    f = np.arange(n_freq, dtype=np.uint64)[:, None]
+    cell = (t * np.uint64(1025) + f) & m32
+    u = _lowbias32(key ^ ((cell * np.uint64(0xC2B2AE35)) & m32))
+    v = keep_probability * 4294967296.0
+    thr = 4294967295 if v >= 4294967295.0 else (0 if v <= 0 else int(v))
+    return u < np.uint64(thr)
+
+
+class RiseOut(NamedTuple):
+    importance_map: Optional[np.ndarray]
+    raw_map: Optional[np.ndarray]
+    baseline_pred: float
+    predictions: Optional[List[float]]
+
+
+def rise_map(y: np.ndarray, predictor, sr: int, n_masks: int, mask_probability: float, seed: int, n_fft: int = 2048,
+             hop_length: int = 512, win_length: int = 2048, baseline_threshold: float = 0.3) -> RiseOut:
+    """``_compute_rise_map`` (:722-806) with the build's mask bits in place of ``np.random.rand``."""
+    y = np.asarray(y, dtype=np.float32)
+    S = dsp.stft(y, n_fft, hop_length, win_length).numpy()
+    baseline_pred = float(predictor.predict(y, sr))
+    if baseline_pred < baseline_threshold:                                      # :741-744
+        return RiseOut(None, None, baseline_pred, None)
+    n_freq, n_time = S.shape
+    importance_map = np.zeros((n_freq, n_time))
+    predictions: List[float] = []
+    for mask_idx in range(n_masks):                                             # :766-790
+        mask = rise_keep_mask(seed, mask_idx, n_freq, n_time, mask_probability).astype(float)
+        y_masked = dsp.istft(S * mask, hop_length, win_length).numpy()
+        if len(y_masked) > len(y):
+            y_masked = y_masked[: len(y)]
+        elif len(y_masked) < len(y):
+            y_masked = np.pad(y_masked, (0, len(y) - len(y_masked)))
+        masked_pred = float(predictor.predict(y_masked, sr))
+        predictions.append(masked_pred)
+        importance_map += mask * masked_pred
+    raw = importance_map / (n_masks * mask_probability + 1e-8)                  # :798
+    norm = (raw - raw.min()) / (raw.max() - raw.min() + 1e-8)                   # :801
+    return RiseOut(norm, raw, baseline_pred, predictions)
