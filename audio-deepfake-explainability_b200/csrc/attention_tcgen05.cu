@@ -393,7 +393,241 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
 }
 
 
-// ----------------------------------------------------------------------------- split-row kernel (production)
+
+// ----------------------------------------------------------------------------- production kernel
+// attention_kernel<256, 1> (one 128-row query tile per CTA, two CTAs per SM, one row per softmax thread, a quarter of the
+// exponentials on the FMA pipe) without the diagnostic plumbing and with the softmax loop software-pipelined across key
+// tiles: the tcgen05.ld of S(j+1) is issued BEFORE the wait on the P(j) stores, so the TMEM read latency (~400 cycles per
+// tile in the traces) hides behind the store drain (~500 cycles) instead of following it.
+//   warps 0-3: softmax;  warp 4: TMA producer;  warp 5: TMEM allocator + tcgen05.mma issuer
+// TMEM columns: S [0,128)  O [128,192)  P [192,256).
+template <bool POLY>
+__global__ void __launch_bounds__(AttCfg<1>::THREADS, 2)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
+    using Cfg = AttCfg<1>;
+    constexpr int STAGES = Cfg::KV_STAGES;
+    constexpr int VARIANT = POLY ? 256 : 0;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + ATT_TILE_BYTES;
+    uint8_t* sV = sK + STAGES * ATT_TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + STAGES;
+    uint64_t* s_full = kv_empty + STAGES;
+    uint64_t* s_free = s_full + 1;
+    uint64_t* p_ready = s_free + 1;
+    uint64_t* pv_done = p_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int head = blockIdx.y, copy = blockIdx.z;
+    const int q0 = blockIdx.x * ATT_TILE;
+    const int nkv = (p.tokens + ATT_TILE - 1) / ATT_TILE;
+    const int hidden = p.heads * ATT_HD;
+
+    if (warp == Cfg::W_TMA && elect_one()) {
+        tma_prefetch_desc(&tmQKV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 4);
+        mbar_init(p_ready, 4);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == Cfg::W_MMA) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == Cfg::W_TMA) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, ATT_TILE_BYTES);
+            tma_load_3d(sQ, &tmQKV, q_full, head * ATT_HD, q0, copy);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j % STAGES;
+                mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
+                tma_load_3d(sK + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], hidden + head * ATT_HD, j * ATT_TILE, copy);
+                tma_load_3d(sV + st * ATT_TILE_BYTES, &tmQKV, &kv_full[st], 2 * hidden + head * ATT_HD, j * ATT_TILE, copy);
+            }
+        }
+    } else if (warp == Cfg::W_MMA) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_TILE, ATT_HD, true);
+            const uint32_t tS = tmem_base + Cfg::S_COL, tO = tmem_base + Cfg::O_COL, tP = tmem_base + Cfg::P_COL;
+            const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+            const uint64_t k_desc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t v_desc0 = make_smem_desc_sw128(smem_u32(sV), 16384, 1024);
+            auto issue_s = [&](int j) {                   // S = Q K_j^T
+                const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
+                const uint32_t idesc_s = make_idesc_bf16(ATT_TILE, nk, false);
+                const uint64_t kd = k_desc0 + static_cast<uint64_t>((j % STAGES) * (ATT_TILE_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, q_desc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(s_full);
+            };
+            auto issue_pv = [&](int j) {                  // O += P V_j
+                const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
+                const uint64_t vd = v_desc0 + static_cast<uint64_t>((j % STAGES) * (ATT_TILE_BYTES >> 4));
+                if (nk == ATT_TILE) {
+#pragma unroll
+                    for (int ks = 0; ks < ATT_TILE / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                } else {
+                    for (int ks = 0; ks < nk / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                }
+                umma_commit(pv_done);
+                umma_commit(&kv_empty[j % STAGES]);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < nkv; ++j) {
+                if (j + 1 < nkv) {
+                    mbar_wait(&kv_full[(j + 1) % STAGES], ((j + 1) / STAGES) & 1);
+                    mbar_wait(s_free, j & 1);
+                    tc_fence_after();
+                    issue_s(j + 1);
+                }
+                mbar_wait(p_ready, j & 1);
+                tc_fence_after();
+                issue_pv(j);
+            }
+        }
+    } else {
+        const int row = warp * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const uint32_t tS = t_lane + Cfg::S_COL, tO = t_lane + Cfg::O_COL, tP = t_lane + Cfg::P_COL;
+        const float c = p.scale_log2;
+        const uint64_t c2 = pack_f32x2(c, c);
+        const uint64_t zero2 = pack_f32x2(p.zero, p.zero);
+        float m_ref = -INFINITY;
+        uint64_t l2 = 0ull, l2b = 0ull;
+        uint32_t r[ATT_TILE];
+        // issue (not wait for) the TMEM loads of score tile j; columns past the last key read as -inf
+        auto load_scores = [&](int j) {
+            const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
+            if (nk == ATT_TILE) {
+                tmem_ld32(tS, r); tmem_ld32(tS + 32, r + 32); tmem_ld32(tS + 64, r + 64); tmem_ld32(tS + 96, r + 96);
+            } else {
+#pragma unroll
+                for (int col = 0; col < ATT_TILE; col += 16) {
+                    if (col < nk) {
+                        tmem_ld16(tS + col, r + col);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[col + i] = 0xff800000u;
+                    }
+                }
+            }
+        };
+        mbar_wait(s_full, 0);
+        tc_fence_after();
+        load_scores(0);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(s_free);
+        for (int j = 0; j < nkv; ++j) {
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < ATT_TILE; i += 8) {
+                m0 = fmax3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                m1 = fmax3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                m2 = fmax3(m2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+                m3 = fmax3(m3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+            }
+            const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            if (j == 0) m_ref = mt;
+            // lazy rescaling: the reference max is replaced (and O, l rescaled) only when this tile exceeds it by 2^8
+            const bool need = (mt - m_ref) * c > ATT_RESCALE_LOG2;
+            bool pv_waited = false;
+            if (__any_sync(0xffffffffu, need)) {
+                if (j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); pv_waited = true; }   // O is quiescent
+                const float m_new = fmaxf(m_ref, mt);
+                const float sc = ex2_approx((m_ref - m_new) * c);
+                l2 = ffma2(l2, pack_f32x2(sc, sc), 0ull);
+                l2b = ffma2(l2b, pack_f32x2(sc, sc), 0ull);
+#pragma unroll
+                for (int cidx = 0; cidx < ATT_HD; cidx += 16) {
+                    uint32_t o[16];
+                    tmem_ld16(tO + cidx, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                    tmem_st16(tO + cidx, o);
+                }
+                m_ref = m_new;
+            }
+            const float mc = m_ref * c;
+            const uint64_t nmc2 = pack_f32x2(-mc, -mc);
+            uint32_t pk[16];
+            exp_chunk<VARIANT>(r, pk, c2, nmc2, zero2, l2, l2b);
+            if (j > 0 && !pv_waited) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }   // P(j-1) . V has retired
+            tmem_st16(tP, pk);
+            exp_chunk<VARIANT>(r + 32, pk, c2, nmc2, zero2, l2, l2b);
+            tmem_st16(tP + 16, pk);
+            exp_chunk<VARIANT>(r + 64, pk, c2, nmc2, zero2, l2, l2b);
+            tmem_st16(tP + 32, pk);
+            exp_chunk<VARIANT>(r + 96, pk, c2, nmc2, zero2, l2, l2b);
+            tmem_st16(tP + 48, pk);
+            const bool more = j + 1 < nkv;
+            if (more) {                                   // S(j+1) was issued when S(j) was released: it is (almost always) there
+                mbar_wait(s_full, (j + 1) & 1);
+                tc_fence_after();
+                load_scores(j + 1);                       // in flight while the P stores drain
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(p_ready);
+            if (more) {
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) mbar_arrive(s_free);
+            }
+        }
+        mbar_wait(pv_done, (nkv - 1) & 1);
+        tc_fence_after();
+        const int q = q0 + row;
+        float la, lb;
+        unpack_f32x2(fadd2(l2, l2b), la, lb);
+        const float inv = 1.0f / (la + lb);
+        uint4 packed[8];
+#pragma unroll
+        for (int cidx = 0; cidx < ATT_HD; cidx += 16) {
+            uint32_t o[16];
+            tmem_ld16(tO + cidx, o);
+            tmem_wait_ld();
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                w[i] = pack_bf16(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+            packed[cidx / 8] = make_uint4(w[0], w[1], w[2], w[3]);
+            packed[cidx / 8 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        if (q < p.tokens) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(copy) * p.tokens + q) * hidden + head * ATT_HD);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = packed[i];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == Cfg::W_MMA) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------- split-row kernel (measured variant)
 // One 128-row query tile per CTA, two CTAs per SM, and TWO threads per query row: softmax warp w (0-7) owns TMEM lanes
 // [32 (w & 3), +32) and the score columns [64 (w >> 2), +64) of every 128-key tile, so each SM sub-partition holds four
 // softmax warps (two per CTA) with short phases instead of two with long ones - the MUFU sees exponential work from
@@ -680,6 +914,19 @@ static int launch_attention_split(const CUtensorMap& tm, const AttnParams& p, di
     return B200X_OK;
 }
 
+template <bool POLY>
+static int launch_attention_fwd(const CUtensorMap& tm, const AttnParams& p, dim3 grid, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_fwd_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<1>::SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_fwd_kernel<POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    attention_fwd_kernel<POLY><<<grid, AttCfg<1>::THREADS, AttCfg<1>::SMEM, s>>>(tm, p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
 // diagnostic only (not part of the public header): select a stripped-down variant of the kernel for bottleneck analysis
 static long long* g_attn_prof = nullptr;
 extern "C" void b200x_debug_attention_variant(int v) { g_attn_dbg = v; }
@@ -699,8 +946,16 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     const uint32_t box[3] = {ATT_HD, ATT_TILE, 1};
     B200X_TRY(make_tmap_bf16(&tm, d_qkv, 3, dims, strides, box));
     AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_prof, 0.0f};
-    dim3 grid(ceil_div(tokens, (g_attn_nq > 0 ? g_attn_nq : 1) * ATT_TILE), heads, copies);
+    dim3 grid(ceil_div(tokens, (g_attn_nq == 2 ? 2 : 1) * ATT_TILE), heads, copies);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (g_attn_nq == 3) {                                  // production kernel (software-pipelined softmax loop)
+        grid.x = ceil_div(tokens, ATT_TILE);
+        switch (g_attn_dbg) {
+            case 0: return launch_attention_fwd<false>(tm, p, grid, s);
+            case 256: return launch_attention_fwd<true>(tm, p, grid, s);
+            default: return set_error(B200X_ERR_INVALID, "attention: unknown variant %d for the production kernel", g_attn_dbg);
+        }
+    }
     if (g_attn_nq == 0) {                                  // split-row kernel: one tile per CTA, two threads per query row
         grid.x = ceil_div(tokens, ATT_TILE);
         switch (g_attn_dbg) {
