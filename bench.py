@@ -154,7 +154,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(n_gpus: int, chunk):
@@ -353,14 +353,30 @@ def run_engine(args):
                     "ms_per_step": ms_host / args.steps},
             "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
 
 
+_RESULT_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: everything libraries print there (NCCL's version banner under torchrun, ...)
+    # is sent to stderr by pointing fd 1 at fd 2 and keeping a private duplicate of the real stdout for emit()
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
