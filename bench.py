@@ -71,8 +71,10 @@ class ClockSampler:
                                            "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
-            time.sleep(0.15)                                 # first sample is in before the timed region starts
-            self.rows.clear()
+            t_end = time.time() + 8.0                        # nvidia-smi needs up to a few seconds to start on an 8-GPU box
+            while not self.rows and time.time() < t_end:
+                time.sleep(0.02)
+            self.rows.clear()                                # samples from here on fall inside the timed region
         except Exception:
             self._proc = None
         return self
