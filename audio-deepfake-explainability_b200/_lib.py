@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200x_engine_window_audio": (C.c_int, [VP, VP, C.c_int, VP, C.c_int64, VP]),
     "b200x_engine_occluded_audio": (C.c_int, [VP, VP, C.c_int, C.c_float, VP]),
     "b200x_engine_band_audio": (C.c_int, [VP, VP, C.c_int, VP]),
+    "b200x_engine_predict_track": (C.c_int, [VP, VP, VP]),
     "b200x_engine_saliency_map": (C.c_int, [VP, VP, VP, C.c_int, VP]),
     "b200x_engine_rise_sweep": (C.c_int, [VP, C.c_int, C.c_int, C.c_uint32, C.c_double, C.c_int, VP]),
     "b200x_engine_rise_audio": (C.c_int, [VP, C.c_int, C.c_int, C.c_uint32, C.c_double, VP]),

@@ -617,13 +617,36 @@ __global__ void base_maxima_kernel(const float* __restrict__ db, int n_frames, i
         if (lane == 0) s_fm[t] = m;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // running maxima by two warps (prefix / suffix), each lane scanning one contiguous segment after a shuffle scan of
+    // the segment maxima (max is exactly associative, so the result does not depend on the split)
+    if (warp < 2) {
+        const int seg = (n_frames + 31) / 32;
+        const int a = min(lane * seg, n_frames), b = min(a + seg, n_frames);
         float m = -INFINITY;
-        for (int t = 0; t <= n_frames; ++t) { pre[t] = m; if (t < n_frames) m = fmaxf(m, s_fm[t]); }
-    } else if (threadIdx.x == 32) {
-        float m = -INFINITY;
-        suf[n_frames] = m;
-        for (int t = n_frames - 1; t >= 0; --t) { m = fmaxf(m, s_fm[t]); suf[t] = m; }
+        for (int t = a; t < b; ++t) m = fmaxf(m, s_fm[t]);
+        if (warp == 0) {
+            float carry = m;                               // inclusive scan of the segment maxima, then shift by one lane
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float v = __shfl_up_sync(0xffffffffu, carry, o);
+                if (lane >= o) carry = fmaxf(carry, v);
+            }
+            float run = __shfl_up_sync(0xffffffffu, carry, 1);
+            if (lane == 0) run = -INFINITY;
+            for (int t = a; t < b; ++t) { pre[t] = run; run = fmaxf(run, s_fm[t]); }
+            if (lane == 31) pre[n_frames] = carry;         // maximum over every frame
+        } else {
+            float carry = m;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float v = __shfl_down_sync(0xffffffffu, carry, o);
+                if (lane + o < 32) carry = fmaxf(carry, v);
+            }
+            float run = __shfl_down_sync(0xffffffffu, carry, 1);
+            if (lane == 31) run = -INFINITY;
+            for (int t = b - 1; t >= a; --t) { run = fmaxf(run, s_fm[t]); suf[t] = run; }
+            if (lane == 0) suf[n_frames] = -INFINITY;
+        }
     }
 }
 

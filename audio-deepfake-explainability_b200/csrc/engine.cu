@@ -480,6 +480,19 @@ extern "C" int b200x_engine_predict(b200x_engine* e, const float* waves, int64_t
     return B200X_OK;
 }
 
+// baseline prediction of the track loaded with set_track, from its device-resident samples (no second upload)
+extern "C" int b200x_engine_predict_track(b200x_engine* e, float* prob, float* logit) {
+    B200X_TRY(check_ready(e, true));
+    B200X_REQUIRE(prob != nullptr, "predict_track: prob is NULL");
+    B200X_TRY(ensure_prob(e, 1));
+    B200X_CUDA_TRY(cudaMemcpyAsync(e->y.p, e->wave.p, e->L * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    B200X_TRY(forward_chunk(e, 1, e->L, nullptr, 0, e->prob.as<float>(), e->logit.as<float>()));
+    B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (logit) B200X_CUDA_TRY(cudaMemcpyAsync(logit, e->logit.p, sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
 extern "C" int b200x_engine_set_track(b200x_engine* e, const float* wave, int64_t n_samples, int on_device) {
     B200X_TRY(check_ready(e, false));
     B200X_REQUIRE(wave != nullptr, "set_track: wave is NULL");

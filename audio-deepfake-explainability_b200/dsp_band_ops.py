@@ -92,7 +92,7 @@ class FrequencyBandPerturbation:
         eng = self.predictor.engine
         sig = np.ascontiguousarray(np.asarray(sig, dtype=np.float32))
         eng.set_track(sig)
-        orig_prob = float(eng.predict(sig))
+        orig_prob = float(eng.predict_track())
         S = eng.spectrogram()
         gains = self.band_gains()
         probs = dist.sharded_sweep(lambda g: eng.fbp_sweep(g, self.normalize_loudness), gains.astype(np.float32))

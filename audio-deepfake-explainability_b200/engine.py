@@ -94,6 +94,12 @@ class Engine:
             return (prob[0], logit[0]) if single else (prob, logit)
         return prob[0] if single else prob
 
+    def predict_track(self) -> float:
+        """Fake-probability of the track loaded with ``set_track`` (device-resident samples, no second upload)."""
+        prob = np.empty(1, np.float32)
+        _lib.check(self.lib.b200x_engine_predict_track(self._h, _ptr(prob), None), "predict_track")
+        return prob[0]
+
     # ------------------------------------------------------------------ track state
     def set_track(self, wave: np.ndarray) -> None:
         w = np.ascontiguousarray(np.asarray(wave, dtype=np.float32))

@@ -149,7 +149,7 @@ class SpectrogramExplainability:
         eng.set_track(y)
         S = eng.spectrogram() if want_spectrogram else None
         S_db = amplitude_to_db_refmax(S) if want_spectrogram else None
-        baseline_pred = float(eng.predict(y))
+        baseline_pred = float(eng.predict_track())
         if verbose:
             print(f"    Baseline prediction: {baseline_pred:.4f}")
         if baseline_pred < baseline_threshold:
@@ -185,7 +185,7 @@ class SpectrogramExplainability:
         eng.set_track(y)
         S = eng.spectrogram()
         S_db = amplitude_to_db_refmax(S)
-        baseline_pred = float(eng.predict(y))
+        baseline_pred = float(eng.predict_track())
         if verbose:
             print(f"    Baseline prediction: {baseline_pred:.4f}")
         if baseline_pred < baseline_threshold:

@@ -235,7 +235,7 @@ def run_engine(args):
 
     def host_step():
         eng.set_track(y_pin.numpy())
-        base = float(eng.predict(y_pin.numpy()))
+        base = float(eng.predict_track())
         prob = eng.occlusion_sweep(win_pin.numpy(), 0.0)
         if world > 1:
             t = torch.from_numpy(prob).cuda()
@@ -245,7 +245,7 @@ def run_engine(args):
         orders = [eng.rank(delta, m) for m in range(4)]
         top = np.unique(np.concatenate([o[:TOP_N] for o in orders]))
         aud = eng.window_audio(windows[top])
-        h2d = 2 * y.nbytes + windows.nbytes + windows.nbytes + delta.nbytes + 4 * delta.nbytes + windows[top].nbytes
+        h2d = y.nbytes + windows.nbytes + windows.nbytes + delta.nbytes + 4 * delta.nbytes + windows[top].nbytes
         d2h = prob.nbytes + 4 + sal.nbytes + 4 * 4 * n_win + sum(a.nbytes for a in aud)
         return h2d, d2h
 

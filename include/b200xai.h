@@ -175,6 +175,9 @@ int b200x_engine_predict(b200x_engine* e, const float* waves, int64_t n_samples,
                          float* logit /* nullable */);
 
 /* Load one track: uploads the wave, computes the explainer STFT (librosa semantics) and keeps both resident. */
+/* fake-probability (and logit, if not NULL) of the track loaded with set_track, read from its device-resident samples:
+ * the baseline prediction of src/spectrogram_explainability.py:605 / dsp_band_ops.py:544 without a second upload */
+int b200x_engine_predict_track(b200x_engine* e, float* prob, float* logit);
 int b200x_engine_set_track(b200x_engine* e, const float* wave, int64_t n_samples, int on_device);
 int b200x_engine_track_shape(b200x_engine* e, int32_t* n_freq, int32_t* n_time);
 /* complex64 [n_freq][n_time] interleaved, the layout of librosa.stft / OcclusionResult.S */

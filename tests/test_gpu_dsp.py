@@ -200,6 +200,10 @@ def test_sparse_occlusion_path_is_bit_identical_to_dense():
     suf = torch.zeros(n_frames + 1, device="cuda")
     ok(lib().b200x_mel_base_maxima(P(db_b), n_frames, 128, P(pre), P(suf), P(None)))
     assert float(suf[0]) == float(db_b.max()) and float(pre[n_frames]) == float(db_b.max())
+    fm = db_b[0, :n_frames].max(dim=1).values.cpu().numpy()                       # per-frame maxima -> running maxima, exactly
+    want_pre = np.concatenate([[-np.inf], np.maximum.accumulate(fm)]).astype(np.float32)
+    want_suf = np.concatenate([np.maximum.accumulate(fm[::-1])[::-1], [-np.inf]]).astype(np.float32)
+    assert np.array_equal(pre.cpu().numpy(), want_pre) and np.array_equal(suf.cpu().numpy(), want_suf)
     rng = torch.zeros(n, 2, dtype=torch.int32, device="cuda")
     ok(lib().b200x_frame_ranges(P(d_w), n, n_frames, P(rng), P(None)))
     max_range = int((wins[:, 1] - wins[:, 0]).max()) + 8
