@@ -247,16 +247,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
             float m_ref = -INFINITY;
             uint64_t l2 = 0ull, l2b = 0ull;               // running row sum, four partial sums
             long long pc_wait = 0, pc_pass = 0, pc_tail = 0, pc_t = 0, pc_ld = 0, pc_max = 0, pc_pv = 0, pc_u = 0;
+            constexpr bool PIPE = (DBG & 65536) != 0;         // S(j+1) is loaded while the P(j) stores drain (see attention_fwd_kernel)
+            uint32_t r[ATT_TILE];
             for (int j = 0; j < nkv; ++j) {
                 const int nk = min(ATT_TILE, p.tokens - j * ATT_TILE);
                 if ((DBG & 32)) pc_t = clock64();
+                if (!PIPE || j == 0) {
                 if (!(DBG & 1024)) mbar_wait(&s_full[x], j & 1);
                 tc_fence_after();
+                }
                 if ((DBG & 32)) { const long long t = clock64(); pc_wait += t - pc_t; pc_t = t; }
                 ATT_TRACE(1, j);
                 // the whole score row into registers, then hand the S buffer back to the tensor pipe at once
-                uint32_t r[ATT_TILE];
-                if ((DBG & 3072) == 1024) {
+                if (PIPE && j > 0) {
+                    // already loaded and released at the end of the previous iteration
+                } else if ((DBG & 3072) == 1024) {
 #pragma unroll
                     for (int i = 0; i < ATT_TILE; ++i) r[i] = __float_as_uint(p.zero * (i + j) - 0.01f * (i + (lane & 7)));
                 } else if ((DBG & 7) != 4) {
@@ -277,9 +282,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 }
                 if ((DBG & 32)) { pc_u = clock64(); pc_ld += pc_u - pc_t; }
                 ATT_TRACE(2, j);
+                if (!PIPE || j == 0) {
                 tc_fence_before();
                 __syncwarp();
                 if (!(DBG & 1024) && elect_one()) mbar_arrive(&s_free[x]);
+                }
                 if ((DBG & 7) != 4) {
                     float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
                     if (!(DBG & 4096) || j == 0)
@@ -352,10 +359,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
                 if ((DBG & 32)) { const long long t = clock64(); pc_pass += t - pc_t; pc_t = t; }
                 ATT_TRACE(5, j);
                 if ((DBG & 32) && j + 1 < nkv) { const bool rdy = mbar_try_wait(&s_full[x], (j + 1) & 1); ATT_TRACE(rdy ? 10 : 9, j); }
+                if (PIPE && j + 1 < nkv) {
+                    mbar_wait(&s_full[x], (j + 1) & 1);
+                    tc_fence_after();
+                    const int nk1 = min(ATT_TILE, p.tokens - (j + 1) * ATT_TILE);
+                    if (nk1 == ATT_TILE) {
+                        tmem_ld32(tS, r); tmem_ld32(tS + 32, r + 32); tmem_ld32(tS + 64, r + 64); tmem_ld32(tS + 96, r + 96);
+                    } else {
+#pragma unroll
+                        for (int col = 0; col < ATT_TILE; col += 16) {
+                            if (col < nk1) {
+                                tmem_ld16(tS + col, r + col);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) r[col + i] = 0xff800000u;
+                            }
+                        }
+                    }
+                }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (!(DBG & 1024) && elect_one()) mbar_arrive(&p_ready[x]);
+                if (PIPE && j + 1 < nkv) {
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (elect_one()) mbar_arrive(&s_free[x]);
+                }
                 if ((DBG & 32)) { const long long t = clock64(); pc_tail += t - pc_t; pc_t = t; }
                 ATT_TRACE(6, j);
             }
@@ -993,6 +1024,9 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
         case 120: return launch_attention<120>(tm, p, grid, s);
         case 512: return launch_attention<512>(tm, p, grid, s);
         case 1024: return launch_attention<1024>(tm, p, grid, s);
+        case 65536: return launch_attention<65536>(tm, p, grid, s);
+        case 65792: return launch_attention<65792>(tm, p, grid, s);
+        case 69888: return launch_attention<69888>(tm, p, grid, s);
         case 4096: return launch_attention<4096>(tm, p, grid, s);
         case 4352: return launch_attention<4352>(tm, p, grid, s);
         case 3072: return launch_attention<3072>(tm, p, grid, s);
