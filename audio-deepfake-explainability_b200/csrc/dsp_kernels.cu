@@ -138,6 +138,8 @@ struct IstftParams {
     int mode;                 // 0 none, 1 occlusion rectangle, 2 per-bin gain, 3 keep only the rectangle
     int hops_per_strip;
     double* sumsq;            // optional [copies]: sum of squares of the written samples (for RMS matching)
+    int copies_per_track;     // copy c reads the spectrogram of track c / copies_per_track ...
+    long long track_stride;   // ... which starts track_stride complex values after the previous track's
     const int* frame_range;   // optional [copies][2]: classifier frames [ma, mb) that differ from the unperturbed track;
                               // only the samples those frames read are synthesised (iSTFT linearity)
 };
@@ -172,6 +174,7 @@ istft_masked_kernel(IstftParams p) {
     }
     const float* gain = MODE == 2 ? p.gains + static_cast<long long>(copy) * NBIN : nullptr;
     float* yout = p.y + static_cast<long long>(copy) * p.out_stride;
+    const float2* spec = p.S + static_cast<long long>(copy / p.copies_per_track) * p.track_stride;
 
     const LaneTrig trig = lane_trig(lane);
     float2 a0[8], a1[8], a2[8];
@@ -190,7 +193,7 @@ istft_masked_kernel(IstftParams p) {
         fence_barrier_init();
         if (t_first < p.n_frames) {
             mbar_expect_tx(&rbar[0], ISTFT_ROW * 8);
-            bulk_load_1d(rowbuf, p.S + static_cast<long long>(t_first) * p.stride, ISTFT_ROW * 8, &rbar[0]);
+            bulk_load_1d(rowbuf, spec + static_cast<long long>(t_first) * p.stride, ISTFT_ROW * 8, &rbar[0]);
         }
     }
     __syncwarp();
@@ -201,7 +204,7 @@ istft_masked_kernel(IstftParams p) {
         if (lane == 0 && t + 1 < hp_b && t + 1 < p.n_frames) {      // the other buffer was read in the previous iteration
             uint64_t* nb = &rbar[(it + 1) & 1];
             mbar_expect_tx(nb, ISTFT_ROW * 8);
-            bulk_load_1d(rowbuf + ((it + 1) & 1) * ISTFT_ROW, p.S + static_cast<long long>(t + 1) * p.stride, ISTFT_ROW * 8, nb);
+            bulk_load_1d(rowbuf + ((it + 1) & 1) * ISTFT_ROW, spec + static_cast<long long>(t + 1) * p.stride, ISTFT_ROW * 8, nb);
         }
         if (t < p.n_frames) {
             mbar_wait(&rbar[it & 1], (it >> 1) & 1);
@@ -299,6 +302,7 @@ struct MelParams {
     long long n_samples;
     const double* sumsq;       // optional RMS matching: per-copy sum of squares of y, and the reference RMS
     double ref_rms;
+    const double* ref_rms_arr; // optional [copies]: per-copy reference RMS (several tracks in one launch); < 0 = leave the copy unscaled
     long long rms_count;
     int n_frames;
     int n_mels;                // <= 128, multiple of 32
@@ -329,7 +333,8 @@ mel_db_kernel(MelParams p) {
     float gain = 1.0f;
     if (p.sumsq != nullptr) {                         // match_rms (src/dsp_band_ops.py:228-233), float64 like the reference
         const double r_x = sqrt(p.sumsq[copy] / static_cast<double>(p.rms_count) + 1e-8);
-        if (!(r_x < 1e-8)) gain = static_cast<float>(p.ref_rms / r_x);
+        const double ref = p.ref_rms_arr != nullptr ? p.ref_rms_arr[copy] : p.ref_rms;
+        if (!(r_x < 1e-8) && ref >= 0.0) gain = static_cast<float>(ref / r_x);
     }
     const LaneTrig trig{};      // unused: this kernel runs at 128 registers / four CTAs per SM, where the table loads of the
                                 // window and the unpack twiddles measured faster (662 us vs 782 us per 64 sparse copies) than computing them
@@ -650,6 +655,26 @@ __global__ void base_maxima_kernel(const float* __restrict__ db, int n_frames, i
     }
 }
 
+// ref[i] = sqrt(mean(wave_i^2) + 1e-8) in float64 (match_rms reference level, src/dsp_band_ops.py:228-233), one CTA per wave;
+// out[i * repeat .. (i + 1) * repeat) all receive it (one entry per perturbed copy of that track)
+__global__ void __launch_bounds__(1024)
+wave_rms_kernel(const float* __restrict__ waves, long long n_samples, long long stride, int repeat, double* __restrict__ out) {
+    __shared__ double s_part[32];
+    const float* w = waves + static_cast<long long>(blockIdx.x) * stride;
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n_samples; i += blockDim.x) { const double v = w[i]; acc += v * v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < static_cast<int>(blockDim.x >> 5); ++i) t += s_part[i];
+        const double r = sqrt(t / static_cast<double>(n_samples) + 1e-8);
+        for (int k = 0; k < repeat; ++k) out[static_cast<long long>(blockIdx.x) * repeat + k] = r;
+    }
+}
+
 // y[b] = sum_i masks[b][i] * stems[i]  (LIME stem recombination, src/lime_explainer.py:283-301)
 __global__ void mix_stems_kernel(const float* __restrict__ stems, long long n_samples, int n_stems,
                                  const unsigned char* __restrict__ masks, float* __restrict__ y, long long y_stride) {
@@ -685,6 +710,15 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
                                   const int32_t* d_windows, float occlusion_value, const float* d_gains, float* d_y,
                                   int64_t y_stride, double* d_sumsq, const int32_t* d_frame_range, int max_range_frames,
                                   void* stream) {
+    return b200x_istft_masked_tracks(d_spec, spec_stride, n_frames, copies, copies > 0 ? copies : 1, 0, mode, d_windows, occlusion_value,
+                                     d_gains, d_y, y_stride, d_sumsq, d_frame_range, max_range_frames, stream);
+}
+
+extern "C" int b200x_istft_masked_tracks(const void* d_spec, int spec_stride, int n_frames, int copies, int copies_per_track,
+                                         int64_t track_stride, int mode, const int32_t* d_windows, float occlusion_value,
+                                         const float* d_gains, float* d_y, int64_t y_stride, double* d_sumsq,
+                                         const int32_t* d_frame_range, int max_range_frames, void* stream) {
+    B200X_REQUIRE(copies_per_track > 0 && track_stride >= 0 && (track_stride * 8) % 16 == 0, "istft: bad track layout");
     B200X_REQUIRE(mode >= 0 && mode <= 4, "istft: bad mode %d", mode);
     B200X_REQUIRE((mode != 1 && mode != 3 && mode != 4) || d_windows != nullptr, "istft: windows missing");
     B200X_REQUIRE(mode != 2 || d_gains != nullptr, "istft: gains missing");
@@ -707,6 +741,7 @@ extern "C" int b200x_istft_masked(const void* d_spec, int spec_stride, int n_fra
     p.out_len = static_cast<long long>(HOP) * (n_frames - 1); p.out_stride = y_stride; p.y = d_y;
     p.windows = d_windows; p.occlusion_value = occlusion_value; p.gains = d_gains; p.mode = mode;
     p.sumsq = d_sumsq; p.frame_range = d_frame_range;
+    p.copies_per_track = copies_per_track; p.track_stride = track_stride;
     B200X_REQUIRE(y_stride >= p.out_len, "istft: y_stride too small");
     B200X_REQUIRE(d_frame_range == nullptr || d_sumsq == nullptr, "istft: sum of squares needs the full signal");
     // hops to synthesise per copy: everything, or what the affected classifier frames read (range + 3 hops)
@@ -802,6 +837,22 @@ extern "C" int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_sample
                             int n_mels, double f_min, double f_max, double amin, const double* d_sumsq,
                             double ref_rms, int64_t rms_count, float* d_db, int db_frames, float* d_cta_max,
                             const int32_t* d_frame_range, int max_range_frames, void* stream) {
+    return b200x_mel_db_ref(d_y, y_stride, n_samples, copies, sample_rate, n_mels, f_min, f_max, amin, d_sumsq, ref_rms, nullptr,
+                            rms_count, d_db, db_frames, d_cta_max, d_frame_range, max_range_frames, stream);
+}
+
+extern "C" int b200x_wave_rms(const float* d_waves, int64_t n_samples, int64_t stride, int n_waves, int repeat, double* d_out,
+                              void* stream) {
+    B200X_REQUIRE(d_waves && d_out && n_samples > 0 && n_waves > 0 && repeat > 0, "wave_rms: bad argument");
+    wave_rms_kernel<<<n_waves, 1024, 0, static_cast<cudaStream_t>(stream)>>>(d_waves, n_samples, stride, repeat, d_out);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+extern "C" int b200x_mel_db_ref(const float* d_y, int64_t y_stride, int64_t n_samples, int copies, int sample_rate,
+                                int n_mels, double f_min, double f_max, double amin, const double* d_sumsq,
+                                double ref_rms, const double* d_ref_rms_per_copy, int64_t rms_count, float* d_db, int db_frames,
+                                float* d_cta_max, const int32_t* d_frame_range, int max_range_frames, void* stream) {
     B200X_REQUIRE(n_mels > 0 && n_mels <= 128 && n_mels % 32 == 0, "mel: n_mels=%d unsupported", n_mels);
     B200X_REQUIRE(n_samples > NFFT / 2 && copies > 0, "mel: bad sizes");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -810,7 +861,7 @@ extern "C" int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_sample
     static bool cfg = false;
     if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEL_SMEM)); cfg = true; }
     MelParams p;
-    p.y = d_y; p.y_stride = y_stride; p.n_samples = n_samples; p.sumsq = d_sumsq; p.ref_rms = ref_rms; p.rms_count = rms_count;
+    p.y = d_y; p.y_stride = y_stride; p.n_samples = n_samples; p.sumsq = d_sumsq; p.ref_rms = ref_rms; p.ref_rms_arr = d_ref_rms_per_copy; p.rms_count = rms_count;
     p.n_frames = 1 + static_cast<int>(n_samples / HOP); p.n_mels = n_mels;
     p.seg_start = g_bank.d_seg_start; p.seg_weights = g_bank.d_seg_weights; p.lane_segments = g_bank.d_lane_segments;
     p.amin = static_cast<float>(amin); p.db = d_db; p.cta_max = d_cta_max; p.frames_per_cta = b200x_mel_frames_per_cta();

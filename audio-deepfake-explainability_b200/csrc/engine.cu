@@ -89,6 +89,8 @@ struct b200x_engine {
     int max_frames = 0, n_cta_max = 0;
     DevBuf y, db, cta_max, partial, floor_v, img_t, img_f, x, h, qkv, att, hid, head_part, prob, logit, sumsq;
     DevBuf windows, gains, masks, stems, delta, order, map;
+    DevBuf S_multi, ref_arr;   // batch-of-tracks FBP: the tracks' spectrograms back to back, per-copy match_rms reference levels
+    const double* ref_arr_cur = nullptr;   // non-null while a multi-track chunk is in flight (forward_chunk_body -> mel)
     int last_copies = 0;
     float* trace = nullptr;
 
@@ -167,9 +169,9 @@ int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const dou
     const int n_cta = ceil_div(span, b200x_mel_frames_per_cta());
     const int D = e->D, T = e->T, M = copies * T;
     e->last_copies = copies;
-    TIMED(KC_MEL, b200x_mel_db(e->y.as<float>(), e->y_stride, n_samples, copies, c.sample_rate, c.n_mels, c.f_min, c.f_max, c.amin,
-                           d_sumsq, e->ref_rms, rms_count, e->db.as<float>(), e->max_frames, e->cta_max.as<float>(), d_ranges,
-                           max_range, s));
+    TIMED(KC_MEL, b200x_mel_db_ref(e->y.as<float>(), e->y_stride, n_samples, copies, c.sample_rate, c.n_mels, c.f_min, c.f_max, c.amin,
+                               d_sumsq, e->ref_rms, e->ref_arr_cur, rms_count, e->db.as<float>(), e->max_frames,
+                               e->cta_max.as<float>(), d_ranges, max_range, s));
     TIMED(KC_RESIZE, b200x_mel_normalize_resize(e->db.as<float>(), e->max_frames, e->cta_max.as<float>(), n_cta, copies, n_frames,
                                          c.n_mels, static_cast<float>(c.top_db), c.std_unbiased, c.norm_eps, c.input_temp_dim,
                                          d_ranges ? e->db_base.as<float>() : nullptr, e->base_pre.as<float>(),
@@ -260,12 +262,13 @@ int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* 
 // reference RMS for match_rms: sqrt(mean(sig^2) + 1e-8) in float64 on the host, like the reference (dsp_band_ops.py:228-233)
 int ensure_ref_rms(b200x_engine* e) {
     if (e->ref_rms >= 0.0) return B200X_OK;
-    std::vector<float> tmp(e->L);
-    B200X_CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->wave.p, e->L * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    B200X_TRY(ensure_grow(e->ref_arr, sizeof(double)));
+    B200X_TRY(b200x_wave_rms(e->wave.as<float>(), e->L, e->L, 1, 1, e->ref_arr.as<double>(), e->stream));
+    e->launches += 1;
+    double r = 0.0;
+    B200X_CUDA_TRY(cudaMemcpyAsync(&r, e->ref_arr.p, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
-    double acc = 0.0;
-    for (int64_t i = 0; i < e->L; ++i) { const double v = tmp[i]; acc += v * v; }
-    e->ref_rms = std::sqrt(acc / static_cast<double>(e->L) + 1e-8);
+    e->ref_rms = r;
     return B200X_OK;
 }
 
@@ -640,6 +643,84 @@ extern "C" int b200x_engine_fbp_sweep(b200x_engine* e, const float* gains, int n
     B200X_TRY(sweep(e, B200X_MASK_BAND_GAIN, n, nullptr, 0.f, d_g, normalize_loudness != 0, e->prob.as<float>()));
     B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+// FBP over a batch of equal-length tracks (BASELINE configs[2]: 64 tracks x the high_resolution bank): the band copies of
+// as many tracks as fit one chunk go through ONE iSTFT launch and ONE classifier forward, the tracks' baselines through a
+// second forward - instead of 13 + 1 copies per launch.  Per-copy arithmetic is that of fbp_sweep / predict, bit for bit.
+extern "C" int b200x_engine_fbp_sweep_tracks(b200x_engine* e, const float* waves, int n_tracks, int64_t n_samples,
+                                             const float* gains, int n_bands, int normalize_loudness, float* base_prob,
+                                             float* prob) {
+    B200X_TRY(check_ready(e, false));
+    if (n_tracks == 0) return B200X_OK;
+    B200X_REQUIRE(waves && gains && base_prob && prob && n_tracks > 0 && n_bands > 0, "fbp_sweep_tracks: bad argument");
+    B200X_REQUIRE(n_samples >= 2048 && n_samples <= e->max_samples, "fbp_sweep_tracks: n_samples=%lld outside [2048, %lld]",
+                  (long long)n_samples, (long long)e->max_samples);
+    B200X_REQUIRE(n_bands <= e->C, "fbp_sweep_tracks: %d bands do not fit a chunk of %d copies", n_bands, e->C);
+    const b200x_model_config& c = e->cfg;
+    const int n_time = 1 + static_cast<int>(n_samples / c.hop_length);
+    const int64_t out_len = static_cast<int64_t>(c.hop_length) * (n_time - 1);
+    const int G = std::max(1, std::min(n_tracks, e->C / n_bands));              // tracks per group
+    const int64_t track_stride = static_cast<int64_t>(n_time) * b200x_engine::s_stride;   // complex values per spectrogram
+    B200X_TRY(ensure_grow(e->S_multi, static_cast<size_t>(G) * track_stride * 2 * sizeof(float)));
+    B200X_TRY(ensure_grow(e->stems, static_cast<size_t>(G) * n_samples * sizeof(float)));
+    B200X_TRY(ensure_grow(e->gains, static_cast<size_t>(G) * n_bands * b200x_engine::n_freq * sizeof(float)));
+    B200X_TRY(ensure_grow(e->ref_arr, static_cast<size_t>(e->C) * sizeof(double)));
+    B200X_TRY(ensure_prob(e, std::max(G * n_bands, G)));
+    // the band table repeats for every track of a group
+    for (int g = 0; g < G; ++g)
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->gains.as<float>() + static_cast<size_t>(g) * n_bands * b200x_engine::n_freq, gains,
+                                       static_cast<size_t>(n_bands) * b200x_engine::n_freq * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    e->baseline_valid = false;
+    for (int t0 = 0; t0 < n_tracks; t0 += G) {
+        const int g_n = std::min(G, n_tracks - t0);
+        const int m = g_n * n_bands;
+        float* d_waves = e->stems.as<float>();
+        B200X_CUDA_TRY(cudaMemcpyAsync(d_waves, waves + static_cast<size_t>(t0) * n_samples, static_cast<size_t>(g_n) * n_samples * sizeof(float),
+                                       cudaMemcpyHostToDevice, e->stream));
+        for (int g = 0; g < g_n; ++g) {
+            B200X_TRY(b200x_stft(d_waves + static_cast<size_t>(g) * n_samples, n_samples, c.n_fft, c.hop_length, 0,
+                                 e->S_multi.as<float>() + static_cast<size_t>(g) * track_stride * 2, b200x_engine::s_stride, e->stream));
+            e->launches += 1;
+        }
+        double* sumsq = nullptr;
+        if (normalize_loudness) {
+            sumsq = e->sumsq.as<double>();
+            B200X_CUDA_TRY(cudaMemsetAsync(sumsq, 0, m * sizeof(double), e->stream));
+            B200X_TRY(b200x_wave_rms(d_waves, n_samples, n_samples, g_n, n_bands, e->ref_arr.as<double>(), e->stream));
+            e->launches += 1;
+        }
+        TIMED(KC_ISTFT, b200x_istft_masked_tracks(e->S_multi.p, b200x_engine::s_stride, n_time, m, n_bands, track_stride, B200X_MASK_BAND_GAIN,
+                                            nullptr, 0.f, e->gains.as<float>(), e->y.as<float>(), e->y_stride, sumsq, nullptr, 0, e->stream));
+        e->launches += 1;
+        e->ref_arr_cur = normalize_loudness ? e->ref_arr.as<double>() : nullptr;
+        const int rc = forward_chunk(e, m, out_len, sumsq, out_len, e->prob.as<float>(), e->logit.as<float>());
+        e->ref_arr_cur = nullptr;
+        B200X_TRY(rc);
+        B200X_CUDA_TRY(cudaMemcpyAsync(prob + static_cast<size_t>(t0) * n_bands, e->prob.p, static_cast<size_t>(m) * sizeof(float),
+                                       cudaMemcpyDeviceToHost, e->stream));
+        // baselines of the group: the tracks themselves (dsp_band_ops.py:544), one forward for all of them
+        B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, static_cast<size_t>(g_n) * e->y_stride * sizeof(float), e->stream));
+        B200X_CUDA_TRY(cudaMemcpy2DAsync(e->y.p, e->y_stride * sizeof(float), d_waves, n_samples * sizeof(float), n_samples * sizeof(float),
+                                         g_n, cudaMemcpyDeviceToDevice, e->stream));
+        B200X_TRY(forward_chunk(e, g_n, n_samples, nullptr, 0, e->prob.as<float>(), e->logit.as<float>()));
+        B200X_CUDA_TRY(cudaMemcpyAsync(base_prob + t0, e->prob.p, static_cast<size_t>(g_n) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        if (t0 + g_n == n_tracks) {
+            // the LAST track of the batch becomes the engine's current track (shape queries, band_map, spectrogram)
+            const int g = g_n - 1;
+            B200X_CUDA_TRY(cudaMemcpyAsync(e->wave.p, d_waves + static_cast<size_t>(g) * n_samples, n_samples * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+            B200X_CUDA_TRY(cudaMemcpyAsync(e->S.p, e->S_multi.as<float>() + static_cast<size_t>(g) * track_stride * 2,
+                                           static_cast<size_t>(track_stride) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+            e->L = n_samples;
+            e->n_time = n_time;
+            e->ref_rms = -1.0;
+            // the tail of every y row beyond hop * (n_time - 1) must read as zero padding again for the occlusion path
+            B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, e->y.bytes, e->stream));
+            B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        }
+    }
     return B200X_OK;
 }
 

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import json
 from pathlib import Path
-from typing import Any, Dict, List, NamedTuple, Optional, Tuple
+from typing import Sequence, Any, Dict, List, NamedTuple, Optional, Tuple
 
 import numpy as np
 
@@ -105,6 +105,29 @@ class FrequencyBandPerturbation:
         rows = grid.band_bin_ranges(self.bands, self.sr, self.n_fft)
         importance_map = eng.band_map(rows, np.asarray(deltas, dtype=np.float64))
         return FBDResult(importance_map, amplitude_to_db_refmax(S), orig_prob, sig, S, batch)
+
+    def compute_importance_batch(self, signals: Sequence[np.ndarray], component_name: str = "mixture") -> List[FBDResult]:
+        """``_compute_component_importance`` for a batch of equal-length signals in shared launches (BASELINE configs[2]:
+        64 tracks x the high_resolution bank).  The reference handles one file at a time (:529-666); here the band copies
+        of as many tracks as fit a chunk go through one iSTFT launch and one classifier forward, with results identical
+        to the per-track call.  ``S`` / ``spectrogram_db`` are not materialised (30 MB per track on the host) - ask the
+        per-track method for them."""
+        if not signals:
+            return []
+        waves = np.stack([np.ascontiguousarray(np.asarray(s, dtype=np.float32)) for s in signals])
+        eng = self.predictor.engine
+        gains = self.band_gains()
+        base, probs = eng.fbp_sweep_tracks(waves, gains.astype(np.float32), self.normalize_loudness)
+        rows = grid.band_bin_ranges(self.bands, self.sr, self.n_fft)
+        out = []
+        for i in range(len(signals)):
+            orig_prob = float(base[i])
+            deltas = [float(orig_prob - float(p)) for p in probs[i]]
+            batch = [{"component": component_name, "low": float(lo), "high": float(hi), "importance": d}
+                     for (lo, hi), d in zip(self.bands, deltas)]
+            importance_map = eng.band_map(rows, np.asarray(deltas, dtype=np.float64))
+            out.append(FBDResult(importance_map, None, orig_prob, waves[i], None, batch))
+        return out
 
     def _save_band_audio(self, sig, gains, deltas, audio_root: Path, component: str, file_name: str) -> None:
         """separated_bands / reversed_separated_bands WAV layout (:608-639)."""

@@ -135,6 +135,19 @@ class Engine:
                    "fbp_sweep")
         return prob
 
+    def fbp_sweep_tracks(self, waves: np.ndarray, gains: np.ndarray, normalize_loudness: bool):
+        """FBP of a batch of equal-length tracks in shared launches: ``(baseline [n_tracks], prob [n_tracks, n_bands])``."""
+        w = np.ascontiguousarray(np.asarray(waves, dtype=np.float32))
+        g = np.ascontiguousarray(np.asarray(gains, dtype=np.float32))
+        if w.ndim != 2 or g.ndim != 2 or g.shape[1] != 1025:
+            raise ValueError(f"waves [n_tracks, L] / gains [n_bands, 1025] expected, got {w.shape} / {g.shape}")
+        base = np.empty(w.shape[0], np.float32)
+        prob = np.empty((w.shape[0], g.shape[0]), np.float32)
+        _lib.check(self.lib.b200x_engine_fbp_sweep_tracks(self._h, _ptr(w), w.shape[0], w.shape[1], _ptr(g), g.shape[0],
+                                                          int(bool(normalize_loudness)), _ptr(base), _ptr(prob)), "fbp_sweep_tracks")
+        self.n_samples = int(w.shape[1])
+        return base, prob
+
     def stem_sweep(self, stems: np.ndarray, masks: np.ndarray) -> np.ndarray:
         s = np.ascontiguousarray(np.asarray(stems, dtype=np.float32))
         m = np.ascontiguousarray(np.asarray(masks) != 0).astype(np.uint8)
@@ -189,7 +202,7 @@ class Engine:
         """``sum_i mask_i * pred_i / (n_masks * p + 1e-8)`` (float64 ``[n_freq, n_time]``, before the min-max scaling)."""
         pr = np.ascontiguousarray(np.asarray(predictions, dtype=np.float64))
         f, t = self.track_shape()
-        out = np.empty((f, t), np.float64)
+        out = _pinned((f, t), np.float64)
         _lib.check(self.lib.b200x_engine_rise_map(self._h, _ptr(pr), pr.shape[0], int(seed) & 0xFFFFFFFF, float(keep_probability),
                                                   _ptr(out)), "rise_map")
         return out
@@ -207,7 +220,7 @@ class Engine:
         r = np.ascontiguousarray(np.asarray(band_rows, dtype=np.int32)).reshape(-1, 2)
         d = np.ascontiguousarray(np.asarray(delta, dtype=np.float64))
         f, t = self.track_shape()
-        out = np.empty((f, t), np.float64)
+        out = _pinned((f, t), np.float64)
         _lib.check(self.lib.b200x_engine_band_map(self._h, _ptr(r), _ptr(d), r.shape[0], _ptr(out)), "band_map")
         return out
 

@@ -69,6 +69,13 @@ int b200x_istft_masked(const void* d_spec, int spec_stride, int n_frames, int co
                        int64_t y_stride, double* d_sumsq, const int32_t* d_frame_range, int max_range_frames,
                        void* stream);
 
+/* Same, for copies that belong to SEVERAL tracks (FBP over a batch of tracks): copy c reads the spectrogram that starts
+ * (c / copies_per_track) * track_stride complex values after d_spec. */
+int b200x_istft_masked_tracks(const void* d_spec, int spec_stride, int n_frames, int copies, int copies_per_track,
+                              int64_t track_stride, int mode, const int32_t* d_windows, float occlusion_value,
+                              const float* d_gains, float* d_y, int64_t y_stride, double* d_sumsq,
+                              const int32_t* d_frame_range, int max_range_frames, void* stream);
+
 /* classifier frames [ma, mb) = [t0 - 4, t1 + 4) whose input samples an occlusion window t0,t1,f0,f1 can change */
 int b200x_frame_ranges(const int32_t* d_windows, int n, int n_frames, int32_t* d_ranges, void* stream);
 
@@ -82,6 +89,14 @@ int b200x_mel_db(const float* d_y, int64_t y_stride, int64_t n_samples, int copi
                  double f_min, double f_max, double amin, const double* d_sumsq, double ref_rms, int64_t rms_count,
                  float* d_db, int db_frames, float* d_cta_max, const int32_t* d_frame_range, int max_range_frames,
                  void* stream);
+/* Same with one reference RMS per copy (d_ref_rms_per_copy[c] < 0 leaves copy c unscaled); NULL = the scalar ref_rms. */
+int b200x_mel_db_ref(const float* d_y, int64_t y_stride, int64_t n_samples, int copies, int sample_rate, int n_mels,
+                     double f_min, double f_max, double amin, const double* d_sumsq, double ref_rms,
+                     const double* d_ref_rms_per_copy, int64_t rms_count, float* d_db, int db_frames, float* d_cta_max,
+                     const int32_t* d_frame_range, int max_range_frames, void* stream);
+/* d_out[i * repeat + k] = sqrt(mean(wave_i^2) + 1e-8), float64: the match_rms reference level (src/dsp_band_ops.py:228-233) */
+int b200x_wave_rms(const float* d_waves, int64_t n_samples, int64_t stride, int n_waves, int repeat, double* d_out, void* stream);
+
 
 /* prefix / suffix maxima of a baseline dB spectrogram: premax[m] = max over frames < m, sufmax[m] = max over frames >= m
  * (m = 0..n_frames), used for the per-copy top_db floor when only frames [ma, mb) were recomputed */
@@ -190,6 +205,12 @@ int b200x_engine_occlusion_sweep(b200x_engine* e, const int32_t* windows, int n,
 /* The FBP hot loop (src/dsp_band_ops.py:573-586) for `n` band gains (float [n][n_freq] = keep + att*(1-keep)). */
 int b200x_engine_fbp_sweep(b200x_engine* e, const float* gains, int n, int normalize_loudness, int on_device,
                            float* prob);
+/* FBP over a batch of equal-length tracks (host buffers): waves float [n_tracks][n_samples], gains float [n_bands][1025]
+ * shared by all tracks; base_prob float [n_tracks] = predict(track), prob float [n_tracks][n_bands].  The band copies of as
+ * many tracks as fit one chunk share one iSTFT launch and one classifier forward; per-copy results are identical to
+ * set_track + predict_track + fbp_sweep track by track.  The last track is left as the engine's current track. */
+int b200x_engine_fbp_sweep_tracks(b200x_engine* e, const float* waves, int n_tracks, int64_t n_samples, const float* gains,
+                                  int n_bands, int normalize_loudness, float* base_prob, float* prob);
 /* AudioLIME recombinations (src/lime_explainer.py:283-301): stems float [n_stems][n_samples], masks uint8 [n][n_stems]. */
 int b200x_engine_stem_sweep(b200x_engine* e, const float* stems, int n_stems, int64_t n_samples, const uint8_t* masks,
                             int n, int on_device, float* prob);

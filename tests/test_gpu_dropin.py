@@ -192,3 +192,26 @@ def test_lime_explain_stems_matches_oracle(predictor, oracle_predictor):
     assert np.abs(np.array([exp.by_feature[n] for n in le.COMPONENT_NAMES_4STEMS])
                   - np.array([ref.by_feature[n] for n in le.COMPONENT_NAMES_4STEMS])).max() < TOL
     assert le.predict_fn_unified(stems.sum(0), predictor).shape == (1, 2)
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_fbp_batch_of_tracks_equals_track_by_track(predictor, normalize):
+    # 5 tracks x 13 bands with copies_per_chunk = 8 ... the fixture's chunk holds no full band bank: use a wider engine
+    p = B200Predictor.random_init(seed=0, copies_per_chunk=32, max_samples=SR * 8)
+    try:
+        fbp = FrequencyBandPerturbation(p, sr=SR, preset="high_resolution", attenuation=0.25, transition_mode="rel", transition_rel=0.2,
+                                        transition_min_hz=5.0, transition_max_hz=500.0, normalize_loudness=normalize)
+        sigs = [synth.synth_track(fam, 2, SR, 6.0) for fam in ("REAL", "SUNO", "SUNO_PRO", "UDIO", "ElevenLabs")]
+        batch = fbp.compute_importance_batch(sigs)            # 2 tracks per group (2 x 13 <= 32): groups of 2, 2, 1
+        assert len(batch) == 5
+        for sig, b in zip(sigs, batch):
+            one = fbp._compute_component_importance(sig, "mixture")
+            assert b.baseline_pred == one.baseline_pred       # same kernels on the same data: not a single bit differs
+            assert [x["importance"] for x in b.batch_importances] == [x["importance"] for x in one.batch_importances]
+            assert np.array_equal(b.importance_map, one.importance_map)
+        assert len({b.baseline_pred for b in batch}) == 5     # the tracks really are different
+        n_freq, n_time = p.engine.track_shape()               # the last track of the batch is the engine's current track
+        assert (n_freq, n_time) == (1025, 1 + len(sigs[-1]) // 512)
+        assert np.abs(p.engine.spectrogram() - one.S).max() == 0
+    finally:
+        p.close()
