@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200x_mel_db_ref": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, VP, C.c_double, VP,
                                     C.c_int64, VP, C.c_int, VP, VP, C.c_int, VP]),
     "b200x_wave_rms": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int, C.c_int, VP, VP]),
+    "b200x_set_traversal": (None, [C.c_int]),
     "b200x_rise_map": (C.c_int, [VP, C.c_int, C.c_uint32, C.c_double, C.c_int, C.c_int, VP, VP]),
     "b200x_band_map": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, VP, VP]),
     "b200x_rank": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "b200x_engine_occluded_audio": (C.c_int, [VP, VP, C.c_int, C.c_float, VP]),
     "b200x_engine_band_audio": (C.c_int, [VP, VP, C.c_int, VP]),
     "b200x_engine_predict_track": (C.c_int, [VP, VP, VP]),
+    "b200x_engine_set_alternate": (C.c_int, [VP, C.c_int]),
     "b200x_engine_fbp_sweep_tracks": (C.c_int, [VP, VP, C.c_int, C.c_int64, VP, C.c_int, C.c_int, VP, VP]),
     "b200x_engine_saliency_map": (C.c_int, [VP, VP, VP, C.c_int, VP]),
     "b200x_engine_rise_sweep": (C.c_int, [VP, C.c_int, C.c_int, C.c_uint32, C.c_double, C.c_int, VP]),

@@ -45,6 +45,7 @@ struct AttnParams {
     float scale_log2;     // (1/sqrt(64)) * log2(e)
     long long* prof;      // diagnostic variant 32: [cta][11 warps][4] cycle counters (else unused)
     float zero;           // always 0.0f: an operand ptxas cannot fold (see exp_chunk)
+    int reverse;          // walk (copy, head) from the end: L2 reuse of the QKV GEMM's last output (see runtime.cu)
 };
 
 // 32 scores (registers r[0..32)) -> p = 2^(s*c - m_ref*c) -> bf16 pairs (round to nearest) -> 16 TMEM columns of P.
@@ -112,7 +113,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int head = blockIdx.y, copy = blockIdx.z;
+    const int head = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, copy = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
     const int q0 = blockIdx.x * NQ * ATT_TILE;
     const int nq = (NQ == 2 && q0 + ATT_TILE < p.tokens) ? 2 : 1;    // query tiles of this block that hold valid rows
     const int nkv = (p.tokens + ATT_TILE - 1) / ATT_TILE;
@@ -976,7 +977,8 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     const uint64_t strides[2] = {static_cast<uint64_t>(width) * 2, static_cast<uint64_t>(width) * 2 * tokens};
     const uint32_t box[3] = {ATT_HD, ATT_TILE, 1};
     B200X_TRY(make_tmap_bf16(&tm, d_qkv, 3, dims, strides, box));
-    AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_prof, 0.0f};
+    AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_prof, 0.0f,
+                 (g_attn_nq == 1 || g_attn_nq == 2) ? g_traverse_reverse : 0};
     dim3 grid(ceil_div(tokens, (g_attn_nq == 2 ? 2 : 1) * ATT_TILE), heads, copies);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (g_attn_nq == 3) {                                  // production kernel (software-pipelined softmax loop)

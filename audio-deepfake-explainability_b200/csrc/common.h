@@ -13,6 +13,7 @@
 namespace b200x {
 
 int set_error(int code, const char* fmt, ...);
+extern int g_traverse_reverse;      // runtime.cu: walk rows / tiles from the end (b200x_set_traversal)
 
 #define B200X_CUDA_TRY(expr)                                                                         \
     do {                                                                                             \

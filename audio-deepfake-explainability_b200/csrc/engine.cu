@@ -90,7 +90,8 @@ struct b200x_engine {
     DevBuf y, db, cta_max, partial, floor_v, img_t, img_f, x, h, qkv, att, hid, head_part, prob, logit, sumsq;
     DevBuf windows, gains, masks, stems, delta, order, map;
     DevBuf S_multi, ref_arr;   // batch-of-tracks FBP: the tracks' spectrograms back to back, per-copy match_rms reference levels
-    const double* ref_arr_cur = nullptr;   // non-null while a multi-track chunk is in flight (forward_chunk_body -> mel)
+    const double* ref_arr_cur = nullptr;
+    bool alternate = true;     // flip the traversal direction between consecutive kernels of the forward (L2 reuse)   // non-null while a multi-track chunk is in flight (forward_chunk_body -> mel)
     int last_copies = 0;
     float* trace = nullptr;
 
@@ -193,25 +194,34 @@ int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const dou
     }
     const size_t xbytes = static_cast<size_t>(M) * D * sizeof(float);
     if (e->trace) B200X_CUDA_TRY(cudaMemcpyAsync(e->trace, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
+    int rev = 1;                          // the first LayerNorm walks forward (rev flips to 0 before its launch)
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
+        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n1_g.as<float>(), w.n1_b.as<float>(), nullptr, nullptr, 0, 0,
                                   c.block_ln_eps, e->h.p, nullptr, s));
+        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
         TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D, D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
                                   c.qkv_bias ? w.qkv_b.as<float>() : nullptr, 0, nullptr, nullptr, 0, 0, 0, s));
+        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
         TIMED(KC_ATTN, b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, s));
+        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
         TIMED(KC_GEMM, b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D, D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
                                   w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
+        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
                                   c.block_ln_eps, e->h.p, nullptr, s));
+        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
         TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp, D), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
                                   w.fc1_b.as<float>(), 1, nullptr, nullptr, 0, 0, 0, s));
+        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
         TIMED(KC_GEMM, b200x_gemm_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, pick_block_n(D), e->x.p, D,
                                   B200X_GEMM_OUT_F32_RESID, w.fc2_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
         e->launches += 7;
         if (e->trace)
             B200X_CUDA_TRY(cudaMemcpyAsync(e->trace + static_cast<size_t>(l + 1) * M * D, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
     }
+    b200x_set_traversal(0);
     TIMED(KC_HEAD, b200x_head(e->x.as<float>(), copies, T, D, e->fn_g.as<float>(), e->fn_b.as<float>(), c.block_ln_eps, c.final_norm,
                          e->cls_w.as<float>(), e->cls_b, e->head_part.as<float>(), d_logit, d_prob, s));
     e->launches += 2;
@@ -969,6 +979,18 @@ extern "C" void* b200x_engine_stream(b200x_engine* e) { return e ? static_cast<v
 extern "C" int b200x_engine_synchronize(b200x_engine* e) {
     B200X_REQUIRE(e != nullptr, "synchronize: engine is NULL");
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_set_alternate(b200x_engine* e, int enable) {
+    if (e == nullptr) return set_error(B200X_ERR_INVALID, "engine is NULL");
+    if (e->alternate != (enable != 0)) {
+        e->alternate = enable != 0;
+        for (auto& kv : e->graphs) {                  // the direction is baked into captured launches: drop the graphs
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        }
+        e->graphs.clear();
+    }
     return B200X_OK;
 }
 

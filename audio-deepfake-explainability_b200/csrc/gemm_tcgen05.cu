@@ -39,6 +39,7 @@ struct GemmParams {
     const float* pe;      // fp32 [group_in, N] (OUT_F32_TOKEN) or null
     int group_in, group_out, group_off;   // out_row = (m / group_in) * group_out + group_off + m % group_in
     long long* prof;      // diagnostic (usually null): per CTA {issuer wait on loads, wait on epilogue, issuer total, tiles}
+    int reverse;          // walk the tile list from its end (L2 reuse of the producer kernel's last output, see runtime.cu)
 };
 
 template <int BN>
@@ -426,7 +427,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                const int tile_e = p.reverse ? num_tiles - 1 - tile : tile;
+                const int m_blk = tile_e / n_tiles, n_blk = tile_e % n_tiles;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -489,7 +491,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         long long pce[4] = {0, 0, 0, 0}, pc_wt = 0, pc_t0 = 0;
         long long* pc = (p.prof != nullptr && warp == 2 && rank == 0) ? pce : nullptr;
         for (int tile = pair; tile < num_tiles; tile += n_pairs, ++tile_parity) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int tile_e = p.reverse ? num_tiles - 1 - tile : tile;
+            const int m_blk = tile_e / n_tiles, n_blk = tile_e % n_tiles;
             if (pc) pc_t0 = clock64();
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
@@ -613,7 +616,7 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
         tmC = tmA;            // unused in token mode
         tmCtail = tmA;
     }
-    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off, g_gemm_prof};
+    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off, g_gemm_prof, pair ? g_traverse_reverse : 0};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (pair) {
         switch (block_n) {

@@ -14,8 +14,9 @@ template <int VPL>   // float4 vectors per lane
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int rows, int D, const float* __restrict__ gamma_a,
                  const float* __restrict__ beta_a, const float* __restrict__ gamma_b, const float* __restrict__ beta_b,
-                 int group, int split, float eps, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                 int group, int split, float eps, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, int reverse) {
+    const int blk = reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+    const int row = blk * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     // rows are grouped (group rows per copy); rows with (row % group) >= split use the second parameter set
@@ -211,7 +212,7 @@ extern "C" int b200x_layernorm(const float* d_x, int rows, int dim, const float*
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = ceil_div(rows, 8);
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(d_out_bf16);
-#define LN_CASE(V) case V: layernorm_kernel<V><<<grid, 256, 0, s>>>(d_x, rows, dim, d_gamma, d_beta, d_gamma2 ? d_gamma2 : d_gamma, d_beta2 ? d_beta2 : d_beta, group, split, eps, ob, d_out_f32); break;
+#define LN_CASE(V) case V: layernorm_kernel<V><<<grid, 256, 0, s>>>(d_x, rows, dim, d_gamma, d_beta, d_gamma2 ? d_gamma2 : d_gamma, d_beta2 ? d_beta2 : d_beta, group, split, eps, ob, d_out_f32, g_traverse_reverse); break;
     switch (dim / 128) { LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
         default: return set_error(B200X_ERR_INVALID, "layernorm: dim=%d not instantiated", dim); }
 #undef LN_CASE

@@ -11,6 +11,11 @@ namespace b200x {
 
 static thread_local char g_err[1024] = "";
 
+// Traversal direction of the NEXT launches of the row / tile-ordered kernels (LayerNorm, GEMM, attention).  The engine flips
+// it between consecutive kernels of the forward: a kernel that walks its rows in the opposite order of its producer starts
+// on the ~100 MB the producer wrote last, which are still in L2 (the 228-copy activations are 0.25-1.1 GB per tensor).
+int g_traverse_reverse = 0;
+
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -110,3 +115,5 @@ extern "C" int b200x_device_count(int* count) {
     B200X_CUDA_TRY(cudaGetDeviceCount(count));
     return B200X_OK;
 }
+
+extern "C" void b200x_set_traversal(int reverse) { b200x::g_traverse_reverse = reverse != 0; }

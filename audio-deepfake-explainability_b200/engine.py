@@ -241,6 +241,10 @@ class Engine:
 
     KERNEL_CLASSES = ("istft", "mel", "resize", "gemm", "attention", "layernorm", "head", "other")
 
+    def set_alternate(self, enable: bool) -> None:
+        """Alternate the row / tile traversal direction between consecutive kernels of the forward (L2 reuse; default on)."""
+        _lib.check(self.lib.b200x_engine_set_alternate(self._h, int(enable)), "set_alternate")
+
     def set_graphs(self, enable: bool) -> None:
         """Replay the per-chunk classifier forward from a CUDA graph (default) or launch kernel by kernel."""
         _lib.check(self.lib.b200x_engine_set_graphs(self._h, int(enable)), "set_graphs")

@@ -190,6 +190,8 @@ def run_engine(args):
 
     cfg = ALPHA_120S
     eng = Engine(cfg, random_state_dict(cfg, 0), copies_per_chunk=args.chunk, max_samples=int(SR * DURATION), device=local)
+    if args.no_alternate:
+        eng.set_alternate(False)
     fam = synth.FAMILIES[rank % len(synth.FAMILIES)]
     y = synth.synth_track(fam, rank // len(synth.FAMILIES), SR, DURATION)
     n_freq, n_time = grid.stft_shape(len(y), 2048, 512)
@@ -387,6 +389,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=228, help="perturbed copies per pass (one chunk = the whole 228-window sweep)")
     ap.add_argument("--cpu-evals", type=int, default=10, help="bounded CPU-baseline sample (perturbed evals)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alternate", action="store_true", help="diagnostic: every kernel walks its rows / tiles forward")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -127,6 +127,11 @@ int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, i
  * [copies*tokens][heads*64].  (F.scaled_dot_product_attention inside the third-party encoder) */
 int b200x_attention(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int head_dim, void* stream);
 
+/* Traversal direction of the following LayerNorm / GEMM (CTA-pair kernel) / attention launches: reverse != 0 walks rows,
+ * tiles and (copy, head) blocks from the end.  Results do not depend on it; the engine alternates it between consecutive
+ * kernels so that each one starts on the part of its input that the previous kernel wrote last and that is still in L2. */
+void b200x_set_traversal(int reverse);
+
 /* LayerNorm over dim (fp32 in); rows with (row % group) >= split use (gamma2, beta2) when group > 0.
  * Exactly one of d_out_bf16 / d_out_f32 (may alias d_x) is non-NULL. */
 int b200x_layernorm(const float* d_x, int rows, int dim, const float* d_gamma, const float* d_beta,
@@ -244,6 +249,9 @@ int64_t b200x_engine_launch_count(b200x_engine* e);
 /* per-kernel-class CUDA-event timing on the engine stream: classes 0 istft, 1 mel, 2 normalise/resize, 3 gemm,
  * 4 attention, 5 layernorm, 6 head, 7 other; get_timing returns the sums since set_timing / the last get (8 entries). */
 int b200x_engine_set_timing(b200x_engine* e, int enable);
+/* Alternate the traversal direction between consecutive kernels of the classifier forward (default on; see
+ * b200x_set_traversal).  Results are unaffected. */
+int b200x_engine_set_alternate(b200x_engine* e, int enable);
 /* The classifier forward of a chunk is replayed from a CUDA graph once its shape has been seen twice (default on);
  * 0 = always launch kernel by kernel.  Results are identical either way. */
 int b200x_engine_set_graphs(b200x_engine* e, int enable);
