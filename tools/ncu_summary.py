@@ -7,7 +7,9 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(io.StringIO(out)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}
-WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+WANT = [("gpu__time_duration.sum", "time"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe %"),
+        ("dram__bytes.sum.per_second", "dram B/s"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("l1tex__m_xbar2l1tex_read_bytes.sum", "l2->sm"),
         ("sm__inst_issued.avg.pct_of_peak_sustained_active", "issue%"), ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
         ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"), ("launch__registers_per_thread", "regs"),
