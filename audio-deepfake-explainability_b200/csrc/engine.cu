@@ -671,13 +671,16 @@ extern "C" int b200x_engine_fbp_sweep_tracks(b200x_engine* e, const float* waves
     const b200x_model_config& c = e->cfg;
     const int n_time = 1 + static_cast<int>(n_samples / c.hop_length);
     const int64_t out_len = static_cast<int64_t>(c.hop_length) * (n_time - 1);
-    const int G = std::max(1, std::min(n_tracks, e->C / n_bands));              // tracks per group
+    // when the iSTFT output is as long as the track (n_samples a multiple of the hop) the baselines ride in the SAME forward as
+    // the band copies (one more copy per track, left unscaled); otherwise they take a forward of their own
+    const bool joint = (out_len == n_samples) && (n_bands + 1 <= e->C);
+    const int G = std::max(1, std::min(n_tracks, e->C / (n_bands + (joint ? 1 : 0))));   // tracks per group
     const int64_t track_stride = static_cast<int64_t>(n_time) * b200x_engine::s_stride;   // complex values per spectrogram
     B200X_TRY(ensure_grow(e->S_multi, static_cast<size_t>(G) * track_stride * 2 * sizeof(float)));
     B200X_TRY(ensure_grow(e->stems, static_cast<size_t>(G) * n_samples * sizeof(float)));
     B200X_TRY(ensure_grow(e->gains, static_cast<size_t>(G) * n_bands * b200x_engine::n_freq * sizeof(float)));
     B200X_TRY(ensure_grow(e->ref_arr, static_cast<size_t>(e->C) * sizeof(double)));
-    B200X_TRY(ensure_prob(e, std::max(G * n_bands, G)));
+    B200X_TRY(ensure_prob(e, G * (n_bands + 1)));
     // the band table repeats for every track of a group
     for (int g = 0; g < G; ++g)
         B200X_CUDA_TRY(cudaMemcpyAsync(e->gains.as<float>() + static_cast<size_t>(g) * n_bands * b200x_engine::n_freq, gains,
@@ -697,25 +700,37 @@ extern "C" int b200x_engine_fbp_sweep_tracks(b200x_engine* e, const float* waves
         double* sumsq = nullptr;
         if (normalize_loudness) {
             sumsq = e->sumsq.as<double>();
-            B200X_CUDA_TRY(cudaMemsetAsync(sumsq, 0, m * sizeof(double), e->stream));
+            B200X_CUDA_TRY(cudaMemsetAsync(sumsq, 0, (m + g_n) * sizeof(double), e->stream));
             B200X_TRY(b200x_wave_rms(d_waves, n_samples, n_samples, g_n, n_bands, e->ref_arr.as<double>(), e->stream));
             e->launches += 1;
+            if (joint) {                                  // reference level -1: the baseline copies are not rescaled
+                std::vector<double> neg(g_n, -1.0);
+                B200X_CUDA_TRY(cudaMemcpyAsync(e->ref_arr.as<double>() + m, neg.data(), g_n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+                B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+            }
         }
         TIMED(KC_ISTFT, b200x_istft_masked_tracks(e->S_multi.p, b200x_engine::s_stride, n_time, m, n_bands, track_stride, B200X_MASK_BAND_GAIN,
                                             nullptr, 0.f, e->gains.as<float>(), e->y.as<float>(), e->y_stride, sumsq, nullptr, 0, e->stream));
         e->launches += 1;
+        if (joint)                                        // baselines = the tracks themselves (dsp_band_ops.py:544), rows m .. m + g_n
+            B200X_CUDA_TRY(cudaMemcpy2DAsync(e->y.as<float>() + static_cast<size_t>(m) * e->y_stride, e->y_stride * sizeof(float), d_waves,
+                                             n_samples * sizeof(float), n_samples * sizeof(float), g_n, cudaMemcpyDeviceToDevice, e->stream));
         e->ref_arr_cur = normalize_loudness ? e->ref_arr.as<double>() : nullptr;
-        const int rc = forward_chunk(e, m, out_len, sumsq, out_len, e->prob.as<float>(), e->logit.as<float>());
+        const int rc = forward_chunk(e, m + (joint ? g_n : 0), out_len, sumsq, out_len, e->prob.as<float>(), e->logit.as<float>());
         e->ref_arr_cur = nullptr;
         B200X_TRY(rc);
         B200X_CUDA_TRY(cudaMemcpyAsync(prob + static_cast<size_t>(t0) * n_bands, e->prob.p, static_cast<size_t>(m) * sizeof(float),
                                        cudaMemcpyDeviceToHost, e->stream));
-        // baselines of the group: the tracks themselves (dsp_band_ops.py:544), one forward for all of them
-        B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, static_cast<size_t>(g_n) * e->y_stride * sizeof(float), e->stream));
-        B200X_CUDA_TRY(cudaMemcpy2DAsync(e->y.p, e->y_stride * sizeof(float), d_waves, n_samples * sizeof(float), n_samples * sizeof(float),
-                                         g_n, cudaMemcpyDeviceToDevice, e->stream));
-        B200X_TRY(forward_chunk(e, g_n, n_samples, nullptr, 0, e->prob.as<float>(), e->logit.as<float>()));
-        B200X_CUDA_TRY(cudaMemcpyAsync(base_prob + t0, e->prob.p, static_cast<size_t>(g_n) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        if (joint) {
+            B200X_CUDA_TRY(cudaMemcpyAsync(base_prob + t0, e->prob.as<float>() + m, static_cast<size_t>(g_n) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        } else {
+            // one forward for all the baselines of the group
+            B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, static_cast<size_t>(g_n) * e->y_stride * sizeof(float), e->stream));
+            B200X_CUDA_TRY(cudaMemcpy2DAsync(e->y.p, e->y_stride * sizeof(float), d_waves, n_samples * sizeof(float), n_samples * sizeof(float),
+                                             g_n, cudaMemcpyDeviceToDevice, e->stream));
+            B200X_TRY(forward_chunk(e, g_n, n_samples, nullptr, 0, e->prob.as<float>(), e->logit.as<float>()));
+            B200X_CUDA_TRY(cudaMemcpyAsync(base_prob + t0, e->prob.p, static_cast<size_t>(g_n) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        }
         B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (t0 + g_n == n_tracks) {
             // the LAST track of the batch becomes the engine's current track (shape queries, band_map, spectrogram)

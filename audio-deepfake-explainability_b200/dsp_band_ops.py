@@ -91,11 +91,18 @@ class FrequencyBandPerturbation:
                                       **_ignored) -> Optional[FBDResult]:
         eng = self.predictor.engine
         sig = np.ascontiguousarray(np.asarray(sig, dtype=np.float32))
-        eng.set_track(sig)
-        orig_prob = float(eng.predict_track())
-        S = eng.spectrogram()
         gains = self.band_gains()
-        probs = dist.sharded_sweep(lambda g: eng.fbp_sweep(g, self.normalize_loudness), gains.astype(np.float32))
+        _, world = dist.world()
+        if world == 1 and len(self.bands) <= eng.copies_per_chunk:
+            # baseline and band copies in one device pass (the baseline rides in the band copies' forward when it can)
+            base, probs2 = eng.fbp_sweep_tracks(sig[None, :], gains.astype(np.float32), self.normalize_loudness)
+            orig_prob, probs = float(base[0]), probs2[0]
+            S = eng.spectrogram()                      # the swept track is the engine's current track
+        else:
+            eng.set_track(sig)
+            orig_prob = float(eng.predict_track())
+            S = eng.spectrogram()
+            probs = dist.sharded_sweep(lambda g: eng.fbp_sweep(g, self.normalize_loudness), gains.astype(np.float32))
         deltas = [float(orig_prob - float(p)) for p in probs]
         if (self.save_perturbed_audio_only or self.save_reversed_perturbed_audio_only) and audio_root is not None:
             self._save_band_audio(sig, gains, deltas, Path(audio_root), component_name, file_name or "track")

@@ -194,14 +194,16 @@ def test_lime_explain_stems_matches_oracle(predictor, oracle_predictor):
     assert le.predict_fn_unified(stems.sum(0), predictor).shape == (1, 2)
 
 
-@pytest.mark.parametrize("normalize", [False, True])
-def test_fbp_batch_of_tracks_equals_track_by_track(predictor, normalize):
+@pytest.mark.parametrize("normalize,seconds", [(False, 6.0), (True, 6.0), (False, 6.4), (True, 6.4)])
+def test_fbp_batch_of_tracks_equals_track_by_track(predictor, normalize, seconds):
+    # 6.4 s = 200 hops: the iSTFT output is as long as the track and the baselines ride in the band copies' forward;
+    # 6.0 s is ragged (187.5 hops): the baselines take a forward of their own
     # 5 tracks x 13 bands with copies_per_chunk = 8 ... the fixture's chunk holds no full band bank: use a wider engine
     p = B200Predictor.random_init(seed=0, copies_per_chunk=32, max_samples=SR * 8)
     try:
         fbp = FrequencyBandPerturbation(p, sr=SR, preset="high_resolution", attenuation=0.25, transition_mode="rel", transition_rel=0.2,
                                         transition_min_hz=5.0, transition_max_hz=500.0, normalize_loudness=normalize)
-        sigs = [synth.synth_track(fam, 2, SR, 6.0) for fam in ("REAL", "SUNO", "SUNO_PRO", "UDIO", "ElevenLabs")]
+        sigs = [synth.synth_track(fam, 2, SR, seconds) for fam in ("REAL", "SUNO", "SUNO_PRO", "UDIO", "ElevenLabs")]
         batch = fbp.compute_importance_batch(sigs)            # 2 tracks per group (2 x 13 <= 32): groups of 2, 2, 1
         assert len(batch) == 5
         for sig, b in zip(sigs, batch):
