@@ -79,6 +79,7 @@ SIGNATURES = {
     "b200x_engine_occluded_audio": (C.c_int, [VP, VP, C.c_int, C.c_float, VP]),
     "b200x_engine_band_audio": (C.c_int, [VP, VP, C.c_int, VP]),
     "b200x_engine_predict_track": (C.c_int, [VP, VP, VP]),
+    "b200x_engine_occlusion_sweep_base": (C.c_int, [VP, VP, C.c_int, C.c_float, C.c_int, VP, VP]),
     "b200x_engine_set_alternate": (C.c_int, [VP, C.c_int]),
     "b200x_engine_fbp_sweep_tracks": (C.c_int, [VP, VP, C.c_int, C.c_int64, VP, C.c_int, C.c_int, VP, VP]),
     "b200x_engine_saliency_map": (C.c_int, [VP, VP, VP, C.c_int, VP]),

@@ -326,9 +326,17 @@ mel_db_kernel(MelParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* tile = dsp_smem + warp * FFT_TILE;
     float2* tw = dsp_smem + DSP_WARPS * FFT_TILE;
+    const int copy = blockIdx.y;
+    {   // CTAs past this copy's frame range have nothing to do (the grid is sized for the widest range of the launch)
+        int lo = 0, hi = p.n_frames;
+        if (p.frame_range != nullptr) { lo = p.frame_range[2 * copy]; hi = p.frame_range[2 * copy + 1]; }
+        if (lo + static_cast<int>(blockIdx.x) * p.frames_per_cta >= hi) {
+            if (threadIdx.x == 0) p.cta_max[static_cast<long long>(copy) * gridDim.x + blockIdx.x] = -INFINITY;
+            return;
+        }
+    }
     fft_fill_twiddles(tw);
     float* pw = reinterpret_cast<float*>(tile);
-    const int copy = blockIdx.y;
     const float* y = p.y + static_cast<long long>(copy) * p.y_stride;
     float gain = 1.0f;
     if (p.sumsq != nullptr) {                         // match_rms (src/dsp_band_ops.py:228-233), float64 like the reference

@@ -91,6 +91,7 @@ struct b200x_engine {
     DevBuf windows, gains, masks, stems, delta, order, map;
     DevBuf S_multi, ref_arr;   // batch-of-tracks FBP: the tracks' spectrograms back to back, per-copy match_rms reference levels
     const double* ref_arr_cur = nullptr;
+    int32_t base_range_host[2] = {0, 0};   // frame range of a baseline copy appended to a sparse chunk (async upload source)
     bool alternate = true;     // flip the traversal direction between consecutive kernels of the forward (L2 reuse)   // non-null while a multi-track chunk is in flight (forward_chunk_body -> mel)
     int last_copies = 0;
     float* trace = nullptr;
@@ -564,8 +565,10 @@ int ensure_baseline(b200x_engine* e) {
 }
 
 // shared body of the occlusion / FBP sweeps: perturb in the iSTFT load stage, classify, collect probabilities
+// with_base: the unperturbed track itself is evaluated as one more copy of the LAST chunk (probability in d_prob_out[n]);
+// on the sparse path that copy carries the full frame range, i.e. it is processed exactly like predict_track's single copy
 int sweep(b200x_engine* e, int mode, int n, const int32_t* d_windows, float occ_value, const float* d_gains, bool rms,
-          float* d_prob_out, int max_range = 0) {
+          float* d_prob_out, int max_range = 0, bool with_base = false) {
     const int64_t out_len = static_cast<int64_t>(e->cfg.hop_length) * (e->n_time - 1);
     // occlusion: only classifier frames [t0-4, t1+4) differ from the unperturbed track (iSTFT linearity); everything
     // else is read from the per-track baseline.  Band gains change every frame, so FBP takes the dense path.
@@ -573,8 +576,13 @@ int sweep(b200x_engine* e, int mode, int n, const int32_t* d_windows, float occ_
     const int32_t* d_ranges = nullptr;
     if (sparse) {
         B200X_TRY(ensure_baseline(e));
-        B200X_TRY(ensure_grow(e->ranges, static_cast<size_t>(n) * 2 * sizeof(int32_t)));
+        B200X_TRY(ensure_grow(e->ranges, static_cast<size_t>(n + 1) * 2 * sizeof(int32_t)));
         const int n_frames_cls = 1 + static_cast<int>(e->L / e->cfg.hop_length);
+        if (with_base) {
+            e->base_range_host[0] = 0;
+            e->base_range_host[1] = n_frames_cls;
+            B200X_CUDA_TRY(cudaMemcpyAsync(e->ranges.as<int32_t>() + 2 * n, e->base_range_host, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        }
         TIMED(KC_OTHER, b200x_frame_ranges(d_windows, n, n_frames_cls, e->ranges.as<int32_t>(), e->stream));
         e->launches += 1;
         d_ranges = e->ranges.as<int32_t>();
@@ -595,19 +603,46 @@ int sweep(b200x_engine* e, int mode, int n, const int32_t* d_windows, float occ_
         if (n_cls > out_len)   // zero padding of the tail (spectrogram_explainability.py:679-680)
             B200X_CUDA_TRY(cudaMemset2DAsync(e->y.as<float>() + out_len, e->y_stride * sizeof(float), 0,
                                              (n_cls - out_len) * sizeof(float), m, e->stream));
-        B200X_TRY(forward_chunk(e, m, n_cls, sumsq, out_len, d_prob_out + c0, e->logit.as<float>() + c0,
-                                d_ranges ? d_ranges + 2 * c0 : nullptr, max_range));
+        const bool add_base = with_base && c0 + m == n && m < e->C && mode == B200X_MASK_OCCLUDE;
+        if (add_base)    // row m of the chunk = the track itself (its tail beyond L is the zero padding every y row keeps)
+            B200X_CUDA_TRY(cudaMemcpyAsync(e->y.as<float>() + static_cast<size_t>(m) * e->y_stride, e->wave.p, e->L * sizeof(float),
+                                           cudaMemcpyDeviceToDevice, e->stream));
+        const int chunk_range = (add_base && sparse) ? 1 + static_cast<int>(e->L / e->cfg.hop_length) : max_range;
+        B200X_TRY(forward_chunk(e, m + (add_base ? 1 : 0), n_cls, sumsq, out_len, d_prob_out + c0, e->logit.as<float>() + c0,
+                                d_ranges ? d_ranges + 2 * c0 : nullptr, chunk_range));
+        if (with_base && c0 + m == n && !add_base) {     // no room in the last chunk: a chunk of its own, like predict_track
+            B200X_CUDA_TRY(cudaMemcpyAsync(e->y.p, e->wave.p, e->L * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+            B200X_TRY(forward_chunk(e, 1, e->L, nullptr, 0, d_prob_out + n, e->logit.as<float>() + n));
+        }
     }
     return B200X_OK;
 }
 }  // namespace
 
+namespace {
+int occlusion_sweep_impl(b200x_engine* e, const int32_t* windows, int n, float occlusion_value, int on_device, float* prob,
+                         float* base_prob);
+}
+
 extern "C" int b200x_engine_occlusion_sweep(b200x_engine* e, const int32_t* windows, int n, float occlusion_value,
                                             int on_device, float* prob) {
+    return occlusion_sweep_impl(e, windows, n, occlusion_value, on_device, prob, nullptr);
+}
+
+extern "C" int b200x_engine_occlusion_sweep_base(b200x_engine* e, const int32_t* windows, int n, float occlusion_value,
+                                                 int on_device, float* prob, float* base_prob) {
+    B200X_REQUIRE(base_prob != nullptr, "occlusion_sweep_base: base_prob is NULL");
+    return occlusion_sweep_impl(e, windows, n, occlusion_value, on_device, prob, base_prob);
+}
+
+namespace {
+int occlusion_sweep_impl(b200x_engine* e, const int32_t* windows, int n, float occlusion_value, int on_device, float* prob,
+                         float* base_prob) {
     B200X_TRY(check_ready(e, true));
-    if (n == 0) return B200X_OK;
+    if (n == 0 && base_prob == nullptr) return B200X_OK;
+    if (n == 0) return b200x_engine_predict_track(e, base_prob, nullptr);
     B200X_REQUIRE(windows && prob && n > 0, "occlusion_sweep: bad argument");
-    B200X_TRY(ensure_prob(e, n));
+    B200X_TRY(ensure_prob(e, n + 1));
     const int32_t* d_win = windows;
     std::vector<int32_t> host_copy;
     const int32_t* h_win = windows;
@@ -630,11 +665,14 @@ extern "C" int b200x_engine_occlusion_sweep(b200x_engine* e, const int32_t* wind
         B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, windows, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, e->stream));
         d_win = e->windows.as<int32_t>();
     }
-    B200X_TRY(sweep(e, B200X_MASK_OCCLUDE, n, d_win, occlusion_value, nullptr, false, e->prob.as<float>(), max_range));
-    B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, e->stream));
+    B200X_TRY(sweep(e, B200X_MASK_OCCLUDE, n, d_win, occlusion_value, nullptr, false, e->prob.as<float>(), max_range, base_prob != nullptr));
+    const cudaMemcpyKind back = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, n * sizeof(float), back, e->stream));
+    if (base_prob) B200X_CUDA_TRY(cudaMemcpyAsync(base_prob, e->prob.as<float>() + n, sizeof(float), back, e->stream));
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
     return B200X_OK;
 }
+}  // namespace
 
 extern "C" int b200x_engine_fbp_sweep(b200x_engine* e, const float* gains, int n, int normalize_loudness, int on_device,
                                       float* prob) {

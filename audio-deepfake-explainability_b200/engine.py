@@ -118,9 +118,16 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ sweeps
-    def occlusion_sweep(self, windows: np.ndarray, occlusion_value: float = 0.0) -> np.ndarray:
+    def occlusion_sweep(self, windows: np.ndarray, occlusion_value: float = 0.0, with_baseline: bool = False):
+        """Fake-probability of every occluded copy; ``with_baseline=True`` also evaluates the track itself in the same
+        device pass and returns ``(prob, baseline)`` with ``baseline == predict_track()`` bit for bit."""
         w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
         prob = np.empty(w.shape[0], np.float32)
+        if with_baseline:
+            base = np.empty(1, np.float32)
+            _lib.check(self.lib.b200x_engine_occlusion_sweep_base(self._h, _ptr(w), w.shape[0], float(occlusion_value), 0, _ptr(prob),
+                                                                  _ptr(base)), "occlusion_sweep_base")
+            return prob, base[0]
         _lib.check(self.lib.b200x_engine_occlusion_sweep(self._h, _ptr(w), w.shape[0], float(occlusion_value), 0, _ptr(prob)),
                    "occlusion_sweep")
         return prob

@@ -115,6 +115,7 @@ class SpectrogramExplainability:
         self.patch_freq_percent, self.stride_freq_percent = patch_freq_percent, stride_freq_percent
         self.use_original_audio = use_original_audio
         self.n_masks, self.mask_probability = n_masks, mask_probability
+        self.speculative_baseline = False   # True: always evaluate the baseline inside the sweep (see occlusion_map_from_wave)
         self.rise_seed = rise_seed          # the reference draws RISE masks from the unseeded numpy global RNG (:768)
         self.highlight_percent, self.abs_threshold = highlight_percent, abs_threshold
         self.checkpoint = SpectrogramCheckpoint(checkpoint_dir) if checkpoint_dir else None
@@ -149,18 +150,28 @@ class SpectrogramExplainability:
         eng.set_track(y)
         S = eng.spectrogram() if want_spectrogram else None
         S_db = amplitude_to_db_refmax(S) if want_spectrogram else None
-        baseline_pred = float(eng.predict_track())
+        n_freq, n_time = eng.track_shape()
+        windows = grid.occlusion_windows(n_freq, n_time, self.patch_time_frames, self.stride_time_frames,
+                                         self.patch_freq_percent, self.stride_freq_percent)
+        _, world = dist.world()
+        # The reference predicts the baseline first and skips the file below the threshold (:605-619).  When nothing can be
+        # skipped (threshold <= 0) - or the caller accepts a wasted sweep on skipped files (speculative_baseline) - the
+        # track rides in the sweep's own device pass as one more copy; the value is predict_track()'s, bit for bit.
+        fused = world == 1 and (baseline_threshold <= 0.0 or self.speculative_baseline)
+        if fused:
+            probs, base = eng.occlusion_sweep(windows, occlusion_value, with_baseline=True)
+            baseline_pred = float(base)
+        else:
+            baseline_pred = float(eng.predict_track())
         if verbose:
             print(f"    Baseline prediction: {baseline_pred:.4f}")
         if baseline_pred < baseline_threshold:
             return OcclusionResult(None, S_db, baseline_pred, y, S, None)
-        n_freq, n_time = eng.track_shape()
-        windows = grid.occlusion_windows(n_freq, n_time, self.patch_time_frames, self.stride_time_frames,
-                                         self.patch_freq_percent, self.stride_freq_percent)
         if verbose:
             print(f"    Processing {len(windows)} patches (t_patch={self.patch_time_frames}, "
                   f"t_stride={self.stride_time_frames}) in one batched sweep...")
-        probs = dist.sharded_sweep(lambda w: eng.occlusion_sweep(w, occlusion_value), windows)
+        if not fused:
+            probs = dist.sharded_sweep(lambda w: eng.occlusion_sweep(w, occlusion_value), windows)
         # importance = baseline_pred - occluded_pred on Python floats (:684)
         importances = [baseline_pred - float(p) for p in probs]
         patch_importances = [

@@ -163,7 +163,7 @@ def workload_config(n_gpus: int, chunk):
     return {"workload": "configs[1]: occlusion sweep, one synthetic 120 s 16 kHz track per GPU, random-init SpecTTTra-alpha-120s, "
                         "1024-frame x 5% window, half-window stride (228 evals) + baseline + saliency map + top-5 window iSTFT",
             "windows_per_track": 228, "tracks": n_gpus, "copies_per_chunk": chunk,
-            "l2_policy": "inputs larger than L2: every step streams the 228-copy activation set (~2.3 GB: residual stream, "
+            "l2_policy": "inputs larger than L2: every step streams the 229-copy activation set (~2.3 GB: residual stream, "
                          "qkv, attention, MLP hidden) plus 228 x 1035 spectrogram rows through the 126 MB L2",
             "parallelism": f"windows/tracks sharded over {n_gpus} GPU(s), one NCCL all-gather of probabilities"}
 
@@ -220,8 +220,8 @@ def run_engine(args):
 
     def device_step():
         _lib.check(lib.b200x_engine_set_track(eng._h, P(d_wave), len(y), 1), "set_track")
-        _lib.check(lib.b200x_engine_predict(eng._h, P(d_wave), len(y), 1, 1, P(d_base), None), "predict")
-        _lib.check(lib.b200x_engine_occlusion_sweep(eng._h, P(d_win), n_win, 0.0, 1, P(d_prob)), "sweep")
+        # baseline prediction + the 228 occluded copies in ONE device pass (the track rides as copy 229 of the chunk)
+        _lib.check(lib.b200x_engine_occlusion_sweep_base(eng._h, P(d_win), n_win, 0.0, 1, P(d_prob), P(d_base)), "sweep")
         if world > 1:
             with torch.cuda.stream(stream):
                 dist.all_gather(gather_buf, d_prob)
@@ -237,8 +237,8 @@ def run_engine(args):
 
     def host_step():
         eng.set_track(y_pin.numpy())
-        base = float(eng.predict_track())
-        prob = eng.occlusion_sweep(win_pin.numpy(), 0.0)
+        prob, base = eng.occlusion_sweep(win_pin.numpy(), 0.0, with_baseline=True)
+        base = float(base)
         if world > 1:
             t = torch.from_numpy(prob).cuda()
             dist.all_gather(gather_buf, t)
@@ -386,7 +386,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--chunk", type=int, default=228, help="perturbed copies per pass (one chunk = the whole 228-window sweep)")
+    ap.add_argument("--chunk", type=int, default=229, help="copies per pass (one chunk = the whole 228-window sweep + the unperturbed track)")
     ap.add_argument("--cpu-evals", type=int, default=10, help="bounded CPU-baseline sample (perturbed evals)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alternate", action="store_true", help="diagnostic: every kernel walks its rows / tiles forward")

@@ -207,6 +207,10 @@ int b200x_engine_get_spectrogram(b200x_engine* e, float* spec_host);
  * prob[i] = predict(istft(S with window i set to occlusion_value)).  Buffers are host (on_device=0) or device. */
 int b200x_engine_occlusion_sweep(b200x_engine* e, const int32_t* windows, int n, float occlusion_value, int on_device,
                                  float* prob);
+/* occlusion_sweep plus the baseline prediction of the track itself (base_prob[0] == predict_track, bit for bit) in the same
+ * device pass: the track rides as one more copy of the last chunk when there is room for it. */
+int b200x_engine_occlusion_sweep_base(b200x_engine* e, const int32_t* windows, int n, float occlusion_value, int on_device,
+                                      float* prob, float* base_prob);
 /* The FBP hot loop (src/dsp_band_ops.py:573-586) for `n` band gains (float [n][n_freq] = keep + att*(1-keep)). */
 int b200x_engine_fbp_sweep(b200x_engine* e, const float* gains, int n, int normalize_loudness, int on_device,
                            float* prob);

@@ -88,6 +88,11 @@ def test_occlusion_sweep_matches_oracle(eng, sd):
     assert np.array_equal(m, loops.saliency_from_windows(sel, delta, n_freq, n_time))
     for mode, key, desc in ((0, abs, True), (1, abs, False), (2, float, True), (3, float, False)):
         assert eng.rank(delta, mode).tolist() == sorted(range(len(delta)), key=lambda i: key(delta[i]), reverse=desc)
+    # baseline inside the sweep (dense path here would be sparse: 256-frame windows on a 750-frame track): same bits as separate calls
+    prob_b, base_b = eng.occlusion_sweep(sel[:3], 0.0, with_baseline=True)          # 3 + 1 copies = one chunk of 4
+    assert np.float32(base_b) == np.float32(base) and np.array_equal(prob_b, prob[:3])
+    prob_b, base_b = eng.occlusion_sweep(sel, 0.0, with_baseline=True)              # 8 windows = 2 full chunks + the baseline alone
+    assert np.float32(base_b) == np.float32(base) and np.array_equal(prob_b, prob)
     # chunking invariance (copies_per_chunk = 4, 8 windows = 2 chunks) and determinism
     assert np.array_equal(prob, eng.occlusion_sweep(sel, 0.0))
     assert np.array_equal(prob[5:6], eng.occlusion_sweep(sel[5:6], 0.0))

@@ -54,6 +54,11 @@ def test_half_stride_sweep_properties(eng, sd, track):
     assert np.array_equal(prob, eng.occlusion_sweep(wins, 0.0))
     sub = np.array([3, 77, 150, 227])
     assert np.array_equal(prob[sub], eng.occlusion_sweep(wins[sub], 0.0))
+    # the baseline evaluated inside the sweep's own device pass is predict_track's, bit for bit, and leaves the windows' bits alone
+    prob_b, base_b = eng.occlusion_sweep(wins[:227], 0.0, with_baseline=True)       # 227 + 1 copies: one chunk of 228
+    assert np.float32(base_b) == np.float32(eng.predict_track()) == np.float32(base) and np.array_equal(prob_b, prob[:227])
+    prob_c, base_c = eng.occlusion_sweep(wins, 0.0, with_baseline=True)             # 228 windows fill the chunk: baseline on its own
+    assert np.float32(base_c) == np.float32(base) and np.array_equal(prob_c, prob)
     # idempotence of the mask: an empty rectangle and a rectangle that restores the original value change nothing
     same = eng.occlusion_sweep(np.array([[512, 512, 100, 151]], np.int32), 0.0)
     assert abs(float(same[0]) - np.float32(base)) < 2e-5        # predict(y) vs predict(iSTFT(STFT(y))), like the reference
