@@ -659,6 +659,202 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) {
     if (warp == Cfg::W_MMA) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// ----------------------------------------------------------------------------- 64-key / in-place-P kernel (measured variant)
+// THREE CTAs per SM instead of two: key tiles of 64, the bf16 P tile written over the score tile it was computed from
+// (S / P 64 columns + O 64 columns = 128 TMEM columns per CTA), 64 KB of shared memory and <= 112 registers per thread.
+// The chain of one CTA is strictly serial - S(j) -> softmax(j) -> P(j).V -> S(j+1), all ordered by the in-order tensor pipe,
+// so neither an "S free" nor a "P.V done" barrier is needed - and the overlap comes from the other two resident CTAs.
+//   warps 0-3: softmax (one query row per thread);  warp 4: TMA producer;  warp 5: TMEM allocator + tcgen05.mma issuer
+struct AttK64 {
+    static constexpr int THREADS = 192, W_TMA = 4, W_MMA = 5, KV = 64, KV_STAGES = 3;
+    static constexpr int KV_BYTES = KV * ATT_HD * 2;                       // 8 KB per K or V tile
+    static constexpr int SMEM = ATT_TILE_BYTES + 2 * KV_STAGES * KV_BYTES + 256;
+    static constexpr uint32_t TMEM_COLS = 128, S_COL = 0, O_COL = 64;       // P aliases S: columns [0, 32)
+};
+
+template <bool POLY>
+__global__ void __launch_bounds__(AttK64::THREADS, 3)
+attention_k64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttnParams p) {
+    using Cfg = AttK64;
+    constexpr int STAGES = Cfg::KV_STAGES, KV = Cfg::KV;
+    constexpr int VARIANT = POLY ? 256 : 0;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + ATT_TILE_BYTES;
+    uint8_t* sV = sK + STAGES * Cfg::KV_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * Cfg::KV_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + STAGES;
+    uint64_t* s_full = kv_empty + STAGES;
+    uint64_t* p_ready = s_full + 1;
+    uint64_t* pv_done = p_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int head = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y, copy = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+    const int q0 = blockIdx.x * ATT_TILE;
+    const int nkv = (p.tokens + KV - 1) / KV;
+    const int hidden = p.heads * ATT_HD;
+
+    if (warp == Cfg::W_TMA && elect_one()) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmKV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 4);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == Cfg::W_MMA) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == Cfg::W_TMA) {
+        if (elect_one()) {
+            mbar_expect_tx(q_full, ATT_TILE_BYTES);
+            tma_load_3d(sQ, &tmQ, q_full, head * ATT_HD, q0, copy);
+            for (int j = 0; j < nkv; ++j) {
+                const int st = j % STAGES;
+                mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[st], 2 * Cfg::KV_BYTES);
+                tma_load_3d(sK + st * Cfg::KV_BYTES, &tmKV, &kv_full[st], hidden + head * ATT_HD, j * KV, copy);
+                tma_load_3d(sV + st * Cfg::KV_BYTES, &tmKV, &kv_full[st], 2 * hidden + head * ATT_HD, j * KV, copy);
+            }
+        }
+    } else if (warp == Cfg::W_MMA) {
+        if (elect_one()) {
+            constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_TILE, ATT_HD, true);
+            const uint32_t tS = tmem_base + Cfg::S_COL, tO = tmem_base + Cfg::O_COL, tP = tmem_base + Cfg::S_COL;
+            const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+            const uint64_t k_desc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+            const uint64_t v_desc0 = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+            mbar_wait(q_full, 0);
+            for (int j = 0; j < nkv; ++j) {
+                const int nk = min(KV, p.tokens - j * KV);
+                const int st = j % STAGES;
+                mbar_wait(&kv_full[st], (j / STAGES) & 1);
+                tc_fence_after();
+                // S(j) = Q K_j^T overwrites the columns P(j-1) was read from by the MMAs just before it (in-order pipe)
+                const uint32_t idesc_s = make_idesc_bf16(ATT_TILE, nk, false);
+                const uint64_t kd = k_desc0 + static_cast<uint64_t>(st * (Cfg::KV_BYTES >> 4));
+#pragma unroll
+                for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, q_desc + 2 * k, kd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(s_full);
+                mbar_wait(p_ready, j & 1);
+                tc_fence_after();
+                const uint64_t vd = v_desc0 + static_cast<uint64_t>(st * (Cfg::KV_BYTES >> 4));
+                for (int ks = 0; ks < nk / 16; ++ks) umma_ts(tO, tP + ks * 8, vd + 128 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
+                umma_commit(pv_done);
+                umma_commit(&kv_empty[st]);
+            }
+        }
+    } else {
+        const int row = warp * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const uint32_t tS = t_lane + Cfg::S_COL, tO = t_lane + Cfg::O_COL, tP = t_lane + Cfg::S_COL;
+        const float c = p.scale_log2;
+        const uint64_t c2 = pack_f32x2(c, c);
+        const uint64_t zero2 = pack_f32x2(p.zero, p.zero);
+        float m_ref = -INFINITY;
+        uint64_t l2 = 0ull, l2b = 0ull;
+        for (int j = 0; j < nkv; ++j) {
+            const int nk = min(KV, p.tokens - j * KV);
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t r[KV];
+            if (nk == KV) {
+                tmem_ld32(tS, r);
+                tmem_ld32(tS + 32, r + 32);
+            } else {
+#pragma unroll
+                for (int col = 0; col < KV; col += 16) {
+                    if (col < nk) {
+                        tmem_ld16(tS + col, r + col);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[col + i] = 0xff800000u;
+                    }
+                }
+            }
+            tmem_wait_ld();
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < KV; i += 8) {
+                m0 = fmax3(m0, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                m1 = fmax3(m1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                m2 = fmax3(m2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+                m3 = fmax3(m3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+            }
+            const float mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            if (j == 0) m_ref = mt;
+            const bool need = (mt - m_ref) * c > ATT_RESCALE_LOG2;
+            if (__any_sync(0xffffffffu, need)) {          // O is quiescent: P(j-1).V retired before S(j) was written
+                const float m_new = fmaxf(m_ref, mt);
+                const float sc = ex2_approx((m_ref - m_new) * c);
+                l2 = ffma2(l2, pack_f32x2(sc, sc), 0ull);
+                l2b = ffma2(l2b, pack_f32x2(sc, sc), 0ull);
+#pragma unroll
+                for (int cidx = 0; cidx < ATT_HD; cidx += 16) {
+                    uint32_t o[16];
+                    tmem_ld16(tO + cidx, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                    tmem_st16(tO + cidx, o);
+                }
+                m_ref = m_new;
+            }
+            const float mc = m_ref * c;
+            const uint64_t nmc2 = pack_f32x2(-mc, -mc);
+            uint32_t pk[16];
+            exp_chunk<VARIANT>(r, pk, c2, nmc2, zero2, l2, l2b);
+            tmem_st16(tP, pk);                            // the whole score row sits in registers: its columns can be reused
+            exp_chunk<VARIANT>(r + 32, pk, c2, nmc2, zero2, l2, l2b);
+            tmem_st16(tP + 16, pk);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(p_ready);
+        }
+        mbar_wait(pv_done, (nkv - 1) & 1);
+        tc_fence_after();
+        const int q = q0 + row;
+        float la, lb;
+        unpack_f32x2(fadd2(l2, l2b), la, lb);
+        const float inv = 1.0f / (la + lb);
+        uint4 packed[8];
+#pragma unroll
+        for (int cidx = 0; cidx < ATT_HD; cidx += 16) {
+            uint32_t o[16];
+            tmem_ld16(tO + cidx, o);
+            tmem_wait_ld();
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                w[i] = pack_bf16(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+            packed[cidx / 8] = make_uint4(w[0], w[1], w[2], w[3]);
+            packed[cidx / 8 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        if (q < p.tokens) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(copy) * p.tokens + q) * hidden + head * ATT_HD);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = packed[i];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == Cfg::W_MMA) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
 // ----------------------------------------------------------------------------- split-row kernel (measured variant)
 // One 128-row query tile per CTA, two CTAs per SM, and TWO threads per query row: softmax warp w (0-7) owns TMEM lanes
 // [32 (w & 3), +32) and the score columns [64 (w >> 2), +64) of every 128-key tile, so each SM sub-partition holds four
@@ -947,6 +1143,19 @@ static int launch_attention_split(const CUtensorMap& tm, const AttnParams& p, di
 }
 
 template <bool POLY>
+static int launch_attention_k64(const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttnParams& p, dim3 grid, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_k64_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttK64::SMEM));
+        B200X_CUDA_TRY(cudaFuncSetAttribute(attention_k64_kernel<POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    attention_k64_kernel<POLY><<<grid, AttK64::THREADS, AttK64::SMEM, s>>>(tmQ, tmKV, p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+template <bool POLY>
 static int launch_attention_fwd(const CUtensorMap& tm, const AttnParams& p, dim3 grid, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
@@ -978,9 +1187,20 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     const uint32_t box[3] = {ATT_HD, ATT_TILE, 1};
     B200X_TRY(make_tmap_bf16(&tm, d_qkv, 3, dims, strides, box));
     AttnParams p{tokens, heads, reinterpret_cast<__nv_bfloat16*>(d_out), 0.125f * 1.4426950408889634f, g_attn_prof, 0.0f,
-                 (g_attn_nq == 1 || g_attn_nq == 2) ? g_traverse_reverse : 0};
+                 (g_attn_nq == 1 || g_attn_nq == 2 || g_attn_nq == 4) ? g_traverse_reverse : 0};
     dim3 grid(ceil_div(tokens, (g_attn_nq == 2 ? 2 : 1) * ATT_TILE), heads, copies);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (g_attn_nq == 4) {                                  // 64-key tiles, P in place, three CTAs per SM
+        CUtensorMap tmKV;
+        const uint32_t box_kv[3] = {ATT_HD, AttK64::KV, 1};
+        B200X_TRY(make_tmap_bf16(&tmKV, d_qkv, 3, dims, strides, box_kv));
+        grid.x = ceil_div(tokens, ATT_TILE);
+        switch (g_attn_dbg) {
+            case 0: return launch_attention_k64<false>(tm, tmKV, p, grid, s);
+            case 256: return launch_attention_k64<true>(tm, tmKV, p, grid, s);
+            default: return set_error(B200X_ERR_INVALID, "attention: unknown variant %d for the 64-key kernel", g_attn_dbg);
+        }
+    }
     if (g_attn_nq == 3) {                                  // production kernel (software-pipelined softmax loop)
         grid.x = ceil_div(tokens, ATT_TILE);
         switch (g_attn_dbg) {
