@@ -316,19 +316,21 @@ def run_engine(args):
     gemm_ms = tim["gemm"][0]
     # DRAM traffic per launch from the committed `ncu --set full` capture of this same command (profiles/): measured on the
     # 228-copy sweep launches; the baseline (1 copy) launches of the same kernel are scaled by their copy count so that the
-    # figure is an average per launch over the same launches as `achieved`
+    # figure is an average per launch over the same launches as `achieved` (ncu captured 228-copy launches)
+    # copies one attention launch handles on average (229 when the baseline rides in the sweep chunk: 12 launches per pass)
+    copies_per_launch = (n_win + 1) * 12.0 * n_pass / dom_n if dom_n else float(n_win + 1)
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_j_ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             t = json.load(f).get("attention_kernel")
         if t:
-            traffic = t["traffic_bytes_per_launch"] * (n_win + 1) / n_win / 2.0
+            traffic = t["traffic_bytes_per_launch"] * copies_per_launch / n_win
             traffic_src = "profiles/r01_j_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of bench.py)"
     roofline = {"bound": "tensor", "kernel": "attention_kernel",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": (n_win + 1) / 2.0 * 1376 * (1152 + 384) * 2,
+                "algorithmic_bytes_per_launch": copies_per_launch * 1376 * (1152 + 384) * 2, "copies_per_launch": copies_per_launch,
                 "peak_source": f"{peaks['source']} (sustained bf16; kernel timed inside a long step)",
                 "avg_launch_ms": dom_ms / dom_n if dom_n else None, "launches": dom_n,
                 "algorithmic_flops_per_launch": flops / dom_n if dom_n else None,
