@@ -7,6 +7,8 @@ the duck-typed ``predictor.predict(wave, sr) -> float`` exactly as the reference
   * top_window_groups ....... src/spectrogram_explainability.py:413-587
   * fbp_component ........... src/dsp_band_ops.py:529-666 (``_compute_component_importance``)
   * stem_mask_probs ......... src/lime_explainer.py:283-301 (``predict_fn_unified``)
+  * rise_map / rise_keep_mask  src/spectrogram_explainability.py:722-806 (``_compute_rise_map``) with the build's counter-based
+                              mask bits in place of the reference's UNSEEDED ``np.random.rand`` (no reference parity can exist)
 
 PARITY STATUS: the loop / indexing / ordering logic here is *pinned*: tests/golden/ref_loops_*.npz were
 produced by running the reference's own functions (imported from /root/reference with its missing
