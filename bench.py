@@ -320,13 +320,14 @@ def run_engine(args):
     # copies one attention launch handles on average (229 when the baseline rides in the sweep chunk: 12 launches per pass)
     copies_per_launch = (n_win + 1) * 12.0 * n_pass / dom_n if dom_n else float(n_win + 1)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_j_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_p_ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            t = json.load(f).get("attention_kernel")
+            tj = json.load(f)
+        t = tj.get("attention_kernel")
         if t:
-            traffic = t["traffic_bytes_per_launch"] * copies_per_launch / n_win
-            traffic_src = "profiles/r01_j_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of bench.py)"
+            traffic = t["traffic_bytes_per_launch"] * copies_per_launch / float(tj.get("_captured_copies_per_launch", n_win + 1))
+            traffic_src = "profiles/r01_p_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of bench.py)"
     roofline = {"bound": "tensor", "kernel": "attention_kernel",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,

@@ -1,5 +1,5 @@
 #!/bin/bash
-# (gpurun copies back at most 64 MiB: the two ncu captures are capped at 16 / 10 kernels)
+# (gpurun copies back at most 64 MiB: the two ncu captures are capped at 10 / 6 kernels)
 # Round validation on one B200: GPU parity tests, smoke, both bench arms, ncu launch list and full captures.
 # usage (under gpurun): bash tools/gpu_validate.sh <tag>
 tag=${1:-x}
@@ -17,11 +17,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 1200 --csv -
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_launches_$tag.log 2>&1
 echo "ncu launches exit $?" | tee -a $out/summary_$tag.txt
 KB_ITERS=1 KB_WARMUP=1 python tools/kernel_bench.py 64 > $out/plain_kb_$tag.log 2>&1 &&
-KB_ITERS=1 KB_WARMUP=1 ncu --set full --clock-control none -k regex:'gemm|attention|layernorm|istft|mel' -c 16 \
+KB_ITERS=1 KB_WARMUP=1 ncu --set full --clock-control none -k regex:'gemm|attention|layernorm|istft|mel' -c 10 \
     -o $out/prof_$tag -f python tools/kernel_bench.py 64 > $out/ncu_full_$tag.log 2>&1
 echo "ncu full exit $?" | tee -a $out/summary_$tag.txt
 # DRAM traffic of the dominant kernels at the bench's own launch shape (228-copy chunk): 2 launches each, skipping the warm-up steps
-ncu --set full --clock-control none -k regex:'attention|gemm2' -s 60 -c 10 \
+ncu --set full --clock-control none -k regex:'attention|gemm2' -s 30 -c 6 \
     -o $out/prof_bench_$tag -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_bench_$tag.log 2>&1
 echo "ncu bench exit $?" | tee -a $out/summary_$tag.txt
 tail -3 $out/pytest_gpu_$tag.log; cat $out/bench_$tag.json; cat $out/kb_$tag.txt $out/kbv_$tag.txt
