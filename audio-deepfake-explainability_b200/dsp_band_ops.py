@@ -73,6 +73,12 @@ class FrequencyBandPerturbation:
         self.save_reversed_perturbed_audio_only = save_reversed_perturbed_audio_only
         self.checkpoint_dir = Path(checkpoint_dir) if checkpoint_dir else None
 
+    @classmethod
+    def from_config(cls, config, predictor, checkpoint_dir=None, save_fbp_audio: str = "none") -> "FrequencyBandPerturbation":
+        """Explainer from a reference YAML file / dict, keys and fallbacks as run_FBP_experiment.py:222-253."""
+        from .config import fbp_kwargs
+        return cls(predictor=predictor, **fbp_kwargs(config, checkpoint_dir, save_fbp_audio))
+
     def _band_transition_width(self, low: float, high: float) -> float:
         return grid.band_transition_width(low, high, self.transition_mode, self.transition_rel, self.transition_min_hz,
                                           self.transition_max_hz, self.transition_hz)

@@ -120,6 +120,12 @@ class SpectrogramExplainability:
         self.highlight_percent, self.abs_threshold = highlight_percent, abs_threshold
         self.checkpoint = SpectrogramCheckpoint(checkpoint_dir) if checkpoint_dir else None
 
+    @classmethod
+    def from_config(cls, config, predictor, checkpoint_dir=None) -> "SpectrogramExplainability":
+        """Explainer from a reference YAML file / dict, keys and fallbacks as run_spectrogram_experiment.py:157-205."""
+        from .config import spectrogram_explainer_kwargs
+        return cls(predictor=predictor, **spectrogram_explainer_kwargs(config, checkpoint_dir))
+
     # -- guards for the variants that have no reference parity (SURVEY.md section 8f) ----------------
     def _require_stft_occlusion(self, method: str = "occlusion") -> None:
         if self.spec_type != "stft":

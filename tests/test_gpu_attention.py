@@ -18,7 +18,7 @@ def _ref(qkv, copies, tokens, heads):
 @pytest.mark.parametrize("copies,tokens,heads,scale", [
     (1, 128, 1, 1.0), (1, 64, 2, 1.0), (2, 272, 2, 1.0), (2, 1376, 6, 1.0), (1, 1376, 6, 6.0),
 ])
-@pytest.mark.parametrize("tiles_per_cta,variant", [(4, 256), (4, 0), (2, 65792), (3, 256), (3, 0), (0, 256), (0, 0), (1, 256), (1, 0), (2, 256), (2, 0)])
+@pytest.mark.parametrize("tiles_per_cta,variant", [(5, 256), (6, 256), (4, 256), (4, 0), (2, 65792), (3, 256), (3, 0), (0, 256), (0, 0), (1, 256), (1, 0), (2, 256), (2, 0)])
 def test_attention_matches_reference(copies, tokens, heads, scale, tiles_per_cta, variant):
     # tiles_per_cta 3 = production kernel (one tile per CTA, software-pipelined softmax loop); 0 = split-row kernel (one tile per CTA, two threads per row); variant 256 = a quarter of the exponentials
     # as an FMA-pipe polynomial
