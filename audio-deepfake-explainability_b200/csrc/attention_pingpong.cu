@@ -47,11 +47,13 @@ struct PPParams {
     float scale_log2;        // (1/sqrt(64)) * log2(e)
     float zero;              // always 0.0f: an operand ptxas cannot fold (see exp32)
     int reverse;             // walk the item list from its end (L2 reuse of the QKV GEMM's last output)
+    long long* prof;         // PROF instantiation only: [cta][16] cycle counters of softmax warp 0 and of the MMA issuer
 };
 
 // 32 scores -> p = 2^(s*c - m*c) -> 16 packed bf16 pairs; row sums into two packed accumulators.  A quarter of the pairs
 // take the FMA-pipe polynomial (exp2_poly2) instead of the MUFU.  The two 16-score halves take their addend through a
 // data dependence on the running sums (value unchanged) so that ptxas keeps the MUFU runs short and interleaved.
+template <int VAR>
 __device__ __forceinline__ void exp32(const uint32_t* r, uint32_t (&pk)[16], uint64_t c2, uint64_t nmc2, uint64_t zero2,
                                       uint64_t& acc_a, uint64_t& acc_b) {
     const uint64_t link_a = ffma2(acc_a, zero2, nmc2);
@@ -59,8 +61,8 @@ __device__ __forceinline__ void exp32(const uint32_t* r, uint32_t (&pk)[16], uin
     for (int i = 0; i < 8; ++i) {
         float x0, x1, p0, p1;
         unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, link_a), x0, x1);
-        if ((i & 3) == 3) exp2_poly2(x0, x1, p0, p1);
-        else { p0 = ex2_approx(x0); p1 = ex2_approx(x1); }
+        if ((VAR & 16) ? (i & 1) : (i & 3) == 3) exp2_poly2(x0, x1, p0, p1);
+        else { p0 = (VAR & 1) ? x0 : ex2_approx(x0); p1 = (VAR & 1) ? x1 : ex2_approx(x1); }
         acc_a = fadd2(acc_a, pack_f32x2(p0, p1));
         pk[i] = pack_bf16(p0, p1);
     }
@@ -69,8 +71,8 @@ __device__ __forceinline__ void exp32(const uint32_t* r, uint32_t (&pk)[16], uin
     for (int i = 8; i < 16; ++i) {
         float x0, x1, p0, p1;
         unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, link_b), x0, x1);
-        if ((i & 3) == 3) exp2_poly2(x0, x1, p0, p1);
-        else { p0 = ex2_approx(x0); p1 = ex2_approx(x1); }
+        if ((VAR & 16) ? (i & 1) : (i & 3) == 3) exp2_poly2(x0, x1, p0, p1);
+        else { p0 = (VAR & 1) ? x0 : ex2_approx(x0); p1 = (VAR & 1) ? x1 : ex2_approx(x1); }
         acc_b = fadd2(acc_b, pack_f32x2(p0, p1));
         pk[i] = pack_bf16(p0, p1);
     }
@@ -100,7 +102,7 @@ __device__ __forceinline__ void mask32(uint32_t* r, int valid) {
     }
 }
 
-template <int SPLIT>
+template <int SPLIT, bool PROF, int VAR>
 __global__ void __launch_bounds__(PPCfg<SPLIT>::THREADS, 1)
 attention_pingpong_kernel(const __grid_constant__ CUtensorMap tmQKV, PPParams p) {
     using Cfg = PPCfg<SPLIT>;
@@ -200,12 +202,16 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tmQKV, PPParams p)
         // ------------------------------------------------------------------ MMA issuer (both streams)
         if (elect_one()) {
             constexpr uint32_t idesc_pv = make_idesc_bf16(PP_TILE, PP_HD, true);
+            long long pc_p = 0, pc_kv = 0, pc_t = 0;
+            const long long pc_start = PROF ? clock64() : 0;
             auto issue_s = [&](int X, int g) {            // S_X = Q_X K^T for step g of stream X
                 const int k = g / nkv, j = g - k * nkv;
+                if (PROF) pc_t = clock64();
                 if (j == 0) mbar_wait(&q_full[X], k & 1);
                 const int st = g % PP_STAGES;
                 mbar_wait(&kv_full[X * PP_STAGES + st], (g / PP_STAGES) & 1);
                 tc_fence_after();
+                if (PROF) pc_kv += clock64() - pc_t;
                 const int nk = min(PP_TILE, p.tokens - j * PP_TILE);
                 const uint32_t idesc_s = make_idesc_bf16(PP_TILE, nk, false);
                 const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + X * PP_TILE_BYTES), 16, 1024);
@@ -238,11 +244,17 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tmQKV, PPParams p)
 #pragma unroll
                 for (int X = 0; X < 2; ++X) {
                     if (g >= steps[X]) continue;
+                    if (PROF) pc_t = clock64();
                     mbar_wait(&p_ready[X], g & 1);        // pass (X, g) is over: S_X is free, P_X is in TMEM
                     tc_fence_after();
+                    if (PROF) pc_p += clock64() - pc_t;
                     if (g + 1 < steps[X]) issue_s(X, g + 1);
                     issue_pv(X, g);
                 }
+            }
+            if (PROF) {
+                long long* o = p.prof + blockIdx.x * 16 + 8;
+                o[0] = pc_p; o[1] = pc_kv; o[2] = clock64() - pc_start; o[3] = max_steps;
             }
         }
     } else {
@@ -255,8 +267,6 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tmQKV, PPParams p)
         const float c = p.scale_log2;
         const uint64_t c2 = pack_f32x2(c, c);
         const uint64_t zero2 = pack_f32x2(p.zero, p.zero);
-        float m_ref[2] = {-INFINITY, -INFINITY};
-        uint64_t la[2] = {0ull, 0ull}, lb[2] = {0ull, 0ull};
         int xn = 0;                                       // exchange counter (SPLIT == 2): buffer parity
         // value of the partner thread (same row, other column half); one named barrier per exchange, alternating buffers
         auto exchange = [&](float v) -> float {
@@ -267,13 +277,13 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tmQKV, PPParams p)
             named_bar_sync(1 + quarter, 64);
             return buf[(half ^ 1) * 128 + row];
         };
-        auto epilogue = [&](int X, int k, int g_last) {   // O_X / l -> bf16 rows of item k
+        auto epilogue = [&](int X, int k, int g_last, uint64_t sum_a, uint64_t sum_b) {   // O_X / l -> bf16 rows of item k
             mbar_wait(&pv_done[X], g_last & 1);
             tc_fence_after();
             int copy, head, qt;
             item_coords(X, k, copy, head, qt);
             float a0, a1;
-            unpack_f32x2(fadd2(la[X], lb[X]), a0, a1);
+            unpack_f32x2(fadd2(sum_a, sum_b), a0, a1);
             float l = a0 + a1;
             if (SPLIT == 2) l += exchange(l);
             const float inv = 1.0f / l;
@@ -298,18 +308,28 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tmQKV, PPParams p)
             }
         };
 
-        for (int g = 0; g < max_steps; ++g) {
-#pragma unroll
-            for (int X = 0; X < 2; ++X) {
-                if (g >= steps[X]) continue;
+        // ONE copy of the pass code serves both streams (X is a run-time value, the per-stream state is swapped between two
+        // register sets) and the rare redo: the loop body must stay well inside the 32 KB instruction cache - with one
+        // softmax warp per scheduler nothing hides an instruction fetch from L2.
+        float m_cur = -INFINITY, m_oth = -INFINITY;
+        uint64_t la_cur = 0ull, lb_cur = 0ull, la_oth = 0ull, lb_oth = 0ull;
+        long long pc_s = 0, pc_first = 0, pc_chunks = 0, pc_pv = 0, pc_tail = 0, pc_t = 0, pc_u = 0, pc_n = 0;
+        const long long pc_start = PROF ? clock64() : 0;
+        const int steps0 = steps[0], steps1 = steps[1];
+#pragma unroll 1
+        for (int hstep = 0; hstep < 2 * max_steps; ++hstep) {
+            const int X = hstep & 1, g = hstep >> 1;
+            if (g < (X ? steps1 : steps0)) {
                 const int k = g / nkv, j = g - k * nkv;
-                if (j == 0 && k > 0) epilogue(X, k - 1, g - 1);
+                if (j == 0 && k > 0) epilogue(X, k - 1, g - 1, la_cur, lb_cur);
                 const int nk = min(PP_TILE, p.tokens - j * PP_TILE);
                 const int vc = min(max(nk - col0, 0), COLS);          // my valid columns (multiple of 16)
                 const uint32_t tS = t_lane + X * PP_TILE + col0;
                 const uint32_t tP = t_lane + 384 + X * PP_HD + col0 / 2;
+                if (PROF) pc_t = clock64();
                 mbar_wait(&s_full[X], g & 1);
                 tc_fence_after();
+                if (PROF) { const long long t = clock64(); pc_s += t - pc_t; pc_t = t; ++pc_n; }
                 uint32_t r[2][32];
                 if (j == 0) {
                     // first key tile of an item: the reference maximum is the tile's true row maximum
@@ -324,77 +344,79 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tmQKV, PPParams p)
                         }
                     }
                     if (SPLIT == 2) mt = fmaxf(mt, exchange(mt));
-                    m_ref[X] = mt;
-                    la[X] = 0ull;
-                    lb[X] = 0ull;
+                    m_cur = mt;
+                    la_cur = 0ull;
+                    lb_cur = 0ull;
                 }
-                const uint64_t la_save = la[X], lb_save = lb[X];
-                float mt = -INFINITY;
-                {
-                    const float mc = m_ref[X] * c;
+                if (PROF) { const long long t = clock64(); pc_first += t - pc_t; pc_t = t; }
+                const uint64_t la_save = la_cur, lb_save = lb_cur;
+#pragma unroll 1
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    float mt = -INFINITY;
+                    const float mc = m_cur * c;
                     const uint64_t nmc2 = pack_f32x2(-mc, -mc);
                     if (vc > 0) tmem_ld32(tS, r[0]);
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch) {
                         if (ch * 32 < vc) {
                             tmem_wait_ld();
-                            if (ch + 1 < NCH && (ch + 1) * 32 < vc) tmem_ld32(tS + (ch + 1) * 32, r[(ch + 1) & 1]);
-                            uint32_t* rc = r[ch & 1];
+                            if (!(VAR & 8) && ch + 1 < NCH && (ch + 1) * 32 < vc) tmem_ld32(tS + (ch + 1) * 32, r[(ch + 1) & 1]);
+                            uint32_t* rc = r[(VAR & 8) ? 0 : (ch & 1)];
                             mask32(rc, vc - ch * 32);
-                            if (j > 0) mt = max32(rc, mt);
+                            if (!(VAR & 4)) mt = max32(rc, mt);
                             uint32_t pk[16];
-                            exp32(rc, pk, c2, nmc2, zero2, la[X], lb[X]);
-                            if (ch == 0 && j > 0) { mbar_wait(&pv_done[X], (g - 1) & 1); tc_fence_after(); }   // P_X(g-1) . V retired
-                            tmem_st16(tP + ch * 16, pk);
-                        }
-                    }
-                    if (vc == 0 && j > 0) { mbar_wait(&pv_done[X], (g - 1) & 1); tc_fence_after(); }
-                }
-                if (j > 0) {
-                    if (SPLIT == 2) mt = fmaxf(mt, exchange(mt));
-                    const bool need = (mt - m_ref[X]) * c > PP_RESCALE_LOG2;
-                    if (__any_sync(0xffffffffu, need)) {
-                        // rare: redo the pass against the new maximum; O and l are rescaled (P.V of this step not issued yet)
-                        const float m_new = fmaxf(m_ref[X], mt);
-                        const float sc = ex2_approx((m_ref[X] - m_new) * c);
-                        tmem_wait_st();
-                        const uint32_t tO = t_lane + 256 + X * PP_HD + half * OCOLS;
-#pragma unroll
-                        for (int cidx = 0; cidx < OCOLS; cidx += 16) {
-                            uint32_t o[16];
-                            tmem_ld16(tO + cidx, o);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
-                            tmem_st16(tO + cidx, o);
-                        }
-                        la[X] = ffma2(la_save, pack_f32x2(sc, sc), 0ull);
-                        lb[X] = ffma2(lb_save, pack_f32x2(sc, sc), 0ull);
-                        m_ref[X] = m_new;
-                        const float mc = m_new * c;
-                        const uint64_t nmc2 = pack_f32x2(-mc, -mc);
-#pragma unroll
-                        for (int ch = 0; ch < NCH; ++ch) {
-                            if (ch * 32 < vc) {
-                                tmem_ld32(tS + ch * 32, r[0]);
-                                tmem_wait_ld();
-                                mask32(r[0], vc - ch * 32);
-                                uint32_t pk[16];
-                                exp32(r[0], pk, c2, nmc2, zero2, la[X], lb[X]);
-                                tmem_st16(tP + ch * 16, pk);
+                            exp32<VAR>(rc, pk, c2, nmc2, zero2, la_cur, lb_cur);
+                            if (ch == 0 && j > 0 && attempt == 0) {                  // P_X(g-1) . V retired
+                                if (PROF) pc_u = clock64();
+                                mbar_wait(&pv_done[X], (g - 1) & 1);
+                                tc_fence_after();
+                                if (PROF) pc_pv += clock64() - pc_u;
                             }
+                            if (!(VAR & 2)) tmem_st16(tP + ch * 16, pk); else asm volatile("" :: "r"(pk[0] ^ pk[5] ^ pk[9] ^ pk[15]));
                         }
                     }
+                    if (j == 0 || attempt == 1) break;
+                    if (vc == 0) { mbar_wait(&pv_done[X], (g - 1) & 1); tc_fence_after(); }
+                    if (SPLIT == 2) mt = fmaxf(mt, exchange(mt));
+                    const bool need = (mt - m_cur) * c > PP_RESCALE_LOG2;
+                    if (!__any_sync(0xffffffffu, need)) break;
+                    // rare: redo the pass against the new maximum; O and l are rescaled (P.V of this step is not issued yet)
+                    const float m_new = fmaxf(m_cur, mt);
+                    const float sc = ex2_approx((m_cur - m_new) * c);
+                    tmem_wait_st();
+                    const uint32_t tO = t_lane + 256 + X * PP_HD + half * OCOLS;
+#pragma unroll
+                    for (int cidx = 0; cidx < OCOLS; cidx += 16) {
+                        uint32_t o[16];
+                        tmem_ld16(tO + cidx, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+                        tmem_st16(tO + cidx, o);
+                    }
+                    la_cur = ffma2(la_save, pack_f32x2(sc, sc), 0ull);
+                    lb_cur = ffma2(lb_save, pack_f32x2(sc, sc), 0ull);
+                    m_cur = m_new;
                 }
+                if (PROF) { const long long t = clock64(); pc_chunks += t - pc_t; pc_t = t; }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (elect_one()) mbar_arrive(&p_ready[X]);
+                if (PROF) pc_tail += clock64() - pc_t;
             }
+            // the other stream's turn
+            const float tm = m_cur; m_cur = m_oth; m_oth = tm;
+            const uint64_t ta = la_cur; la_cur = la_oth; la_oth = ta;
+            const uint64_t tb = lb_cur; lb_cur = lb_oth; lb_oth = tb;
         }
-#pragma unroll
-        for (int X = 0; X < 2; ++X)
-            if (steps[X] > 0) epilogue(X, n_k[X] - 1, steps[X] - 1);
+        // after 2 * max_steps half steps the "current" set belongs to stream 0 again
+        if (steps0 > 0) epilogue(0, n_k[0] - 1, steps0 - 1, la_cur, lb_cur);
+        if (steps1 > 0) epilogue(1, n_k[1] - 1, steps1 - 1, la_oth, lb_oth);
+        if (PROF && warp == 0 && lane == 0) {
+            long long* o = p.prof + blockIdx.x * 16;
+            o[0] = pc_s; o[1] = pc_first; o[2] = pc_chunks; o[3] = pc_pv; o[4] = pc_tail; o[5] = clock64() - pc_start; o[6] = pc_n;
+        }
     }
 
     tc_fence_before();
@@ -402,16 +424,17 @@ attention_pingpong_kernel(const __grid_constant__ CUtensorMap tmQKV, PPParams p)
     if (warp == Cfg::W_MMA) tmem_dealloc<512>(tmem_base);
 }
 
-template <int SPLIT>
+template <int SPLIT, bool PROF, int VAR = 0>
 static int launch_pingpong(const CUtensorMap& tm, const PPParams& p, int grid, cudaStream_t s) {
     using Cfg = PPCfg<SPLIT>;
-    B200X_CUDA_TRY(cudaFuncSetAttribute(attention_pingpong_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attention_pingpong_kernel<SPLIT><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm, p);
+    B200X_CUDA_TRY(cudaFuncSetAttribute(attention_pingpong_kernel<SPLIT, PROF, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attention_pingpong_kernel<SPLIT, PROF, VAR><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm, p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }
 
-int attention_pingpong(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int split, int reverse, cudaStream_t s) {
+int attention_pingpong(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int split, int reverse, long long* prof,
+                       int var, cudaStream_t s) {
     const int width = 3 * heads * PP_HD;
     CUtensorMap tm;
     const uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(tokens), static_cast<uint64_t>(copies)};
@@ -428,11 +451,25 @@ int attention_pingpong(const void* d_qkv, void* d_out, int copies, int tokens, i
     p.scale_log2 = 0.125f * 1.4426950408889634f;
     p.zero = 0.0f;
     p.reverse = reverse;
+    p.prof = prof;
     int dev = 0, sms = 0;
     B200X_CUDA_TRY(cudaGetDevice(&dev));
     B200X_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = std::min(sms, ceil_div(p.n_items, 2));
-    return split == 2 ? launch_pingpong<2>(tm, p, grid, s) : launch_pingpong<1>(tm, p, grid, s);
+    if (split == 1) {
+        switch (var) {
+            case 1: return launch_pingpong<1, false, 1>(tm, p, grid, s);
+            case 2: return launch_pingpong<1, false, 2>(tm, p, grid, s);
+            case 3: return launch_pingpong<1, false, 3>(tm, p, grid, s);
+            case 4: return launch_pingpong<1, false, 4>(tm, p, grid, s);
+            case 8: return launch_pingpong<1, false, 8>(tm, p, grid, s);
+            case 15: return launch_pingpong<1, false, 15>(tm, p, grid, s);
+            case 16: return launch_pingpong<1, false, 16>(tm, p, grid, s);
+            default: break;
+        }
+    }
+    if (prof != nullptr) return split == 2 ? launch_pingpong<2, true>(tm, p, grid, s) : launch_pingpong<1, true>(tm, p, grid, s);
+    return split == 2 ? launch_pingpong<2, false>(tm, p, grid, s) : launch_pingpong<1, false>(tm, p, grid, s);
 }
 
 }  // namespace b200x

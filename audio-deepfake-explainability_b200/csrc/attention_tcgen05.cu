@@ -1110,7 +1110,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKV, AttnParams p) 
 }  // namespace b200x
 
 using namespace b200x;
-namespace b200x { int attention_pingpong(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int split, int reverse, cudaStream_t s); }
+namespace b200x { int attention_pingpong(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int split, int reverse, long long* prof, int var, cudaStream_t s); }
 
 // production configuration: one query tile per CTA (two CTAs per SM) with a quarter of the exponentials on the FMA pipe
 // (variant bit 256); the other variants are diagnostics selected through the two b200x_debug_* setters below
@@ -1192,7 +1192,7 @@ extern "C" int b200x_attention(const void* d_qkv, void* d_out, int copies, int t
     dim3 grid(ceil_div(tokens, (g_attn_nq == 2 ? 2 : 1) * ATT_TILE), heads, copies);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (g_attn_nq == 5 || g_attn_nq == 6)                  // ping-pong kernel (attention_pingpong.cu), 4 or 8 softmax warps
-        return attention_pingpong(d_qkv, d_out, copies, tokens, heads, g_attn_nq - 4, g_traverse_reverse, s);
+        return attention_pingpong(d_qkv, d_out, copies, tokens, heads, g_attn_nq - 4, g_traverse_reverse, g_attn_prof, g_attn_dbg == 256 ? 0 : g_attn_dbg, s);
     if (g_attn_nq == 4) {                                  // 64-key tiles, P in place, three CTAs per SM
         CUtensorMap tmKV;
         const uint32_t box_kv[3] = {ATT_HD, AttK64::KV, 1};

@@ -14,7 +14,7 @@ from typing import Sequence, Any, Dict, List, NamedTuple, Optional, Tuple
 import numpy as np
 
 from . import dist, grid
-from .audio_io import load_audio, write_wav
+from .audio_io import AudioDecodeError, load_audio, write_wav
 from .grid import FREQUENCY_BAND_PRESETS, smooth_band_keep_mask  # noqa: F401  (re-exported like the reference module)
 from .sonics_api import B200Predictor
 from .spectrogram_explainability import amplitude_to_db_refmax
@@ -216,7 +216,11 @@ class FrequencyBandPerturbation:
             if max_samples_per_model:
                 files = files[:max_samples_per_model]
             for audio_file in files:
-                res = self.process_audio_file(str(audio_file), bands_dir, folder.name)
+                try:
+                    res = self.process_audio_file(str(audio_file), bands_dir, folder.name)
+                except AudioDecodeError as e:           # undecodable file: log it and go on (no checkpoint mark)
+                    print(f"    Skipping {audio_file.name}: {e}")
+                    continue
                 if res:
                     flat = {k: v for k, v in res.items() if k != "components"}
                     rows.append(flat)

@@ -137,13 +137,46 @@ def stable_order(keys: np.ndarray, descending: bool) -> np.ndarray:
     return np.argsort(keys, kind="stable")
 
 
-def topk_window_groups(importances: Sequence[float], top_n: int) -> Dict[str, np.ndarray]:
+def snap_ties(importances: Sequence[float], tie_epsilon: float) -> np.ndarray:
+    """Ranking keys with ``|v| < tie_epsilon`` snapped to exactly 0.0 (builder extension, off at 0.0).
+
+    The reference ranks the raw floats (:428-434, 566-571).  Windows whose occlusion changes nothing (e.g. bins above a
+    track's band limit) have ``|delta|`` at the arithmetic noise floor of the classifier (exactly 0.0 in fp32 eager
+    PyTorch, ~1e-5 with bf16 GEMM inputs), so their mutual order - which decides the *worst* group - is not reproducible
+    between two arithmetics, including reference CPU vs reference CUDA.  With a ``tie_epsilon`` above that noise floor such
+    windows are exact ties and keep grid order (Python's stable sort), on every implementation."""
+    imp = np.array(importances, dtype=np.float64)
+    if tie_epsilon > 0.0:
+        imp[np.abs(imp) < tie_epsilon] = 0.0
+    return imp
+
+
+def topk_boundary_margins(importances: Sequence[float], top_n: int) -> Dict[str, float]:
+    """Gap between the last key inside each top-``top_n`` group and the first key outside it (inf if nothing is outside).
+    A group is reproducible across arithmetics whose per-window error is below half of its margin."""
+    imp = np.asarray(importances, dtype=np.float64)
+    a_desc = np.sort(np.abs(imp))[::-1]
+    a_asc = a_desc[::-1]
+    pos = np.sort(imp[imp > 0])[::-1]
+    neg = np.sort(imp[imp < 0])
+
+    def gap(keys, asc):
+        if len(keys) <= top_n or top_n <= 0:
+            return float("inf")
+        return float(keys[top_n] - keys[top_n - 1]) if asc else float(keys[top_n - 1] - keys[top_n])
+
+    return {"best": gap(a_desc, False), "worst": gap(a_asc, True),
+            "most_influential": min(gap(pos, False), gap(neg, True))}
+
+
+def topk_window_groups(importances: Sequence[float], top_n: int, tie_epsilon: float = 0.0) -> Dict[str, np.ndarray]:
     """Indices (into the window list) of the reference's four groups, in output (rank) order.
 
     all: abs desc; best: top_n abs desc; worst: top_n abs asc; most_influential: top_n positives by
     value desc ++ top_n negatives by value asc, the concatenation re-sorted by abs asc (:515-587).
+    ``tie_epsilon`` > 0 ranks ``snap_ties(importances, tie_epsilon)`` instead of the raw values.
     """
-    imp = np.asarray(importances, dtype=np.float64)
+    imp = snap_ties(importances, tie_epsilon)
     a = np.abs(imp)
     all_desc = stable_order(a, True)
     asc = stable_order(a, False)

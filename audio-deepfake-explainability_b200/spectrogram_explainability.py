@@ -16,7 +16,7 @@ from typing import Any, Dict, NamedTuple, Optional
 import numpy as np
 
 from . import dist, grid
-from .audio_io import load_audio, write_wav
+from .audio_io import AudioDecodeError, load_audio, write_wav
 from .sonics_api import B200Predictor
 
 
@@ -97,7 +97,7 @@ class SpectrogramExplainability:
                  use_original_audio: bool = True, patch_time_frames: int = 2048, stride_time_frames: int = 2048,
                  patch_freq_percent: float = 25.0, stride_freq_percent: float = 25.0, n_masks: int = 500,
                  mask_probability: float = 0.5, checkpoint_dir=None, highlight_percent: float = 20.0,
-                 abs_threshold: float = 0.0, rise_seed: int = 0):
+                 abs_threshold: float = 0.0, rise_seed: int = 0, tie_epsilon: float = 0.0):
         if not isinstance(predictor, B200Predictor):
             raise TypeError("the B200 occlusion sweep needs a B200Predictor (the classifier runs inside the sweep); "
                             f"got {type(predictor).__name__}")
@@ -117,6 +117,7 @@ class SpectrogramExplainability:
         self.n_masks, self.mask_probability = n_masks, mask_probability
         self.speculative_baseline = False   # True: always evaluate the baseline inside the sweep (see occlusion_map_from_wave)
         self.rise_seed = rise_seed          # the reference draws RISE masks from the unseeded numpy global RNG (:768)
+        self.tie_epsilon = float(tie_epsilon)   # 0.0 = rank the raw importances like the reference; see grid.snap_ties
         self.highlight_percent, self.abs_threshold = highlight_percent, abs_threshold
         self.checkpoint = SpectrogramCheckpoint(checkpoint_dir) if checkpoint_dir else None
 
@@ -229,7 +230,8 @@ class SpectrogramExplainability:
     # -- top-k windows -> JSON / WAV ----------------------------------------------------------------------
     def top_window_groups(self, patch_importances: list, top_n: int, file_name: str) -> Dict[str, dict]:
         """Metadata payloads of the four groups (all / best / worst / most_influential), ranks as in :413-587."""
-        imp = np.array([p["importance"] for p in patch_importances], dtype=np.float64)
+        raw = np.array([p["importance"] for p in patch_importances], dtype=np.float64)
+        imp = grid.snap_ties(raw, self.tie_epsilon)      # ranking keys only; the JSON reports the raw values
         eng = self.predictor.engine
         order_desc = eng.rank(imp, 0)                    # |imp| descending, stable
         order_asc = eng.rank(imp, 1)                     # |imp| ascending, stable
@@ -341,7 +343,11 @@ class SpectrogramExplainability:
             if max_samples_per_model:
                 files = files[:max_samples_per_model]
             for audio_file in files:
-                res = self.process_audio_file(str(audio_file), saliency_dir, baseline_threshold, folder.name)
+                try:
+                    res = self.process_audio_file(str(audio_file), saliency_dir, baseline_threshold, folder.name)
+                except AudioDecodeError as e:           # undecodable file: log it and go on (no checkpoint mark)
+                    print(f"    Skipping {audio_file.name}: {e}")
+                    continue
                 if res:
                     results.append(res)
                     if rank == 0:

@@ -11,13 +11,19 @@ from audio_deepfake_explainability_b200.weights import ALPHA_120S, random_state_
 from oracle import loops
 
 
-def test_float_wav_round_trip_and_duration(tmp_path):
+def test_pcm16_wav_round_trip_and_duration(tmp_path):
     y = (0.3 * np.sin(2 * np.pi * 440 * np.arange(32000) / 16000)).astype(np.float32)
     write_wav(tmp_path / "a.wav", y, 16000)
+    rate, raw = wavfile.read(str(tmp_path / "a.wav"))
+    assert rate == 16000 and raw.dtype == np.int16                     # soundfile.write(path, y, sr) default subtype: PCM_16 (:494)
+    want = np.clip(np.rint(y.astype(np.float64) * 32768.0), -32768, 32767) / 32768.0
     back, sr = load_audio(tmp_path / "a.wav", sr=16000)
-    assert sr == 16000 and back.dtype == np.float32 and np.array_equal(back, y)
+    assert sr == 16000 and back.dtype == np.float32 and np.array_equal(back, want.astype(np.float32))
+    assert np.abs(back - y).max() <= 0.5 / 32768 + 1e-9
+    write_wav(tmp_path / "clip.wav", np.array([1.5, -1.5, 1.0, -1.0]), 16000)
+    assert wavfile.read(str(tmp_path / "clip.wav"))[1].tolist() == [32767, -32768, 32767, -32768]
     cut, _ = load_audio(tmp_path / "a.wav", sr=16000, duration=0.5)
-    assert np.array_equal(cut, y[:8000])                               # duration trims BEFORE resampling, like librosa
+    assert np.array_equal(cut, back[:8000])                            # duration trims BEFORE resampling, like librosa
     native, sr = load_audio(tmp_path / "a.wav", sr=None)
     assert sr == 16000 and len(native) == 32000
 
@@ -38,9 +44,13 @@ def test_int16_stereo_downmix_and_resample(tmp_path):
 
 
 def test_unsupported_container_is_an_error(tmp_path):
+    from audio_deepfake_explainability_b200.audio_io import AudioDecodeError
     (tmp_path / "x.mp3").write_bytes(b"ID3")
-    with pytest.raises(RuntimeError):
+    with pytest.raises(AudioDecodeError):
         load_audio(tmp_path / "x.mp3")
+    (tmp_path / "bad.wav").write_bytes(b"not a wav file")
+    with pytest.raises(AudioDecodeError):
+        load_audio(tmp_path / "bad.wav")
 
 
 def test_alpha_120s_configuration_and_state_dict_layout():
