@@ -48,19 +48,19 @@ SIGNATURES = {
                                              C.c_float, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, VP]),
     "b200x_mix_stems": (C.c_int, [VP, C.c_int64, C.c_int, VP, C.c_int, VP, C.c_int64, VP]),
     "b200x_gemm_bf16": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_int, C.c_int,
-                                  VP, C.c_int, VP, VP, C.c_int, C.c_int, C.c_int, VP]),
-    "b200x_attention": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP]),
-    "b200x_layernorm": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP, C.c_int, C.c_int, C.c_float, VP, VP, VP]),
+                                  VP, C.c_int, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP]),
+    "b200x_attention": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP]),
+    "b200x_layernorm": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP, C.c_int, C.c_int, C.c_float, VP, VP, C.c_int, VP]),
     "b200x_head_slices": (C.c_int, []),
     "b200x_head": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, VP, VP, C.c_float, C.c_int, VP, C.c_float, VP, VP, VP, VP]),
     "b200x_delta": (C.c_int, [VP, C.c_float, C.c_int, VP, VP]),
+    "b200x_delta_dev": (C.c_int, [VP, VP, C.c_int, VP, VP]),
     "b200x_saliency_reduce": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, VP, VP]),
     "b200x_istft_masked_tracks": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, VP, C.c_float, VP, VP, C.c_int64, VP, VP,
                                              C.c_int, VP]),
     "b200x_mel_db_ref": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, VP, C.c_double, VP,
                                     C.c_int64, VP, C.c_int, VP, VP, C.c_int, VP]),
     "b200x_wave_rms": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int, C.c_int, VP, VP]),
-    "b200x_set_traversal": (None, [C.c_int]),
     "b200x_rise_map": (C.c_int, [VP, C.c_int, C.c_uint32, C.c_double, C.c_int, C.c_int, VP, VP]),
     "b200x_band_map": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, VP, VP]),
     "b200x_rank": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),

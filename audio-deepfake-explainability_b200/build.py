@@ -59,7 +59,10 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs), "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs), "-cudart", "shared",
+           # the CUDA runtime is resolved at load time (the process normally has torch's libcudart.so.12 mapped already);
+           # RUNPATH covers a bare `ctypes.CDLL` without LD_LIBRARY_PATH
+           "-Xlinker", "-rpath=/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/cuda_runtime/lib:/usr/local/cuda/lib64"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")

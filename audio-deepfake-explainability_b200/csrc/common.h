@@ -13,7 +13,15 @@
 namespace b200x {
 
 int set_error(int code, const char* fmt, ...);
-extern int g_traverse_reverse;      // runtime.cu: walk rows / tiles from the end (b200x_set_traversal)
+
+// Per-DEVICE one-time state (runtime.cu).  Several engines on different GPUs may live in one process and be driven from
+// different host threads: nothing below is cached process-wide.
+//   ensure_kernel_smem : cudaFuncSetAttribute(MaxDynamicSharedMemorySize [+ carveout]) once per (device, kernel)
+//   device_sm_count    : multiprocessor count of the current device
+//   device_first_use   : true exactly once per (current device, key): guard for lazily initialised device tables
+int ensure_kernel_smem(const void* func, int bytes, bool max_carveout = false);
+int device_sm_count(int* sms);
+int device_first_use(const void* key, bool* first);
 
 #define B200X_CUDA_TRY(expr)                                                                         \
     do {                                                                                             \

@@ -11,6 +11,7 @@
 // All FFTs are warp-level (fft.cuh); HBM/L2 traffic is coalesced float2 / float4.
 #include <algorithm>
 #include <cmath>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -48,15 +49,16 @@ __global__ void init_tables_kernel() {
     }
 }
 
+// the __device__ tables live once per device (module instance): initialise them on first use of EACH device
 static int ensure_tables(cudaStream_t stream) {
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [&] {
-        init_tables_kernel<<<8, 256, 0, stream>>>();
-        err = cudaGetLastError();
-        if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
-    });
-    if (err != cudaSuccess) return set_error(B200X_ERR_CUDA, "table init failed: %s", cudaGetErrorString(err));
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);                  // a second host thread must not launch before the tables are filled
+    bool first = false;
+    B200X_TRY(device_first_use(reinterpret_cast<const void*>(init_tables_kernel), &first));
+    if (!first) return B200X_OK;
+    init_tables_kernel<<<8, 256, 0, stream>>>();
+    B200X_CUDA_TRY(cudaGetLastError());
+    B200X_CUDA_TRY(cudaStreamSynchronize(stream));
     return B200X_OK;
 }
 
@@ -705,8 +707,7 @@ extern "C" int b200x_stft(const float* d_wave, int64_t n_samples, int n_fft, int
     B200X_REQUIRE(n_samples > NFFT / 2 && spec_stride >= NBIN, "stft: bad sizes");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     B200X_TRY(ensure_tables(s));
-    static bool cfg = false;
-    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DSP_SMEM)); cfg = true; }
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(stft_kernel), DSP_SMEM));
     const int n_frames = 1 + static_cast<int>(n_samples / HOP);
     const int grid = std::min(ceil_div(n_frames, DSP_WARPS), 148 * 8);
     stft_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(d_wave, n_samples, n_frames, reflect_pad, reinterpret_cast<float2*>(d_spec), spec_stride);
@@ -735,15 +736,11 @@ extern "C" int b200x_istft_masked_tracks(const void* d_spec, int spec_stride, in
                   "istft: spectrogram rows must be 16-byte aligned with stride >= %d complex values (got %d)", ISTFT_ROW, spec_stride);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     B200X_TRY(ensure_tables(s));
-    static bool cfg = false;
-    if (!cfg) {
-        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
-        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
-        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
-        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
-        B200X_CUDA_TRY(cudaFuncSetAttribute(istft_masked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ISTFT_SMEM));
-        cfg = true;
-    }
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(istft_masked_kernel<0>), ISTFT_SMEM));
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(istft_masked_kernel<1>), ISTFT_SMEM));
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(istft_masked_kernel<2>), ISTFT_SMEM));
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(istft_masked_kernel<3>), ISTFT_SMEM));
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(istft_masked_kernel<4>), ISTFT_SMEM));
     IstftParams p;
     p.S = reinterpret_cast<const float2*>(d_spec); p.stride = spec_stride; p.n_frames = n_frames;
     p.out_len = static_cast<long long>(HOP) * (n_frames - 1); p.out_stride = y_stride; p.y = d_y;
@@ -776,14 +773,23 @@ struct MelBank {
     int *d_seg_start = nullptr, *d_lane_segments = nullptr;
     float2* d_seg_weights = nullptr;
 };
-static MelBank g_bank;
-static double g_bank_key[4] = {0, 0, 0, 0};
+struct MelBankSlot { MelBank bank; double key[3] = {0, 0, 0}; };
+static std::map<int, MelBankSlot> g_banks;                 // one filterbank per DEVICE (its pointers are device allocations)
+static std::mutex g_bank_mutex;
 
 // HTK triangular filters, unnormalised (torchaudio melscale_fbanks(norm=None, mel_scale="htk")): w[f][k] =
 // max(0, min(rising, falling)) in double, rounded to float.  Stored by segment (see MelParams).
-static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_max) {
-    if (g_bank.n_mels == n_mels && g_bank_key[0] == sample_rate && g_bank_key[1] == f_min && g_bank_key[2] == f_max)
+static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_max, MelBank* out) {
+    int dev = 0;
+    B200X_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    MelBankSlot& slot = g_banks[dev];
+    MelBank& g_bank = slot.bank;
+    double* g_bank_key = slot.key;
+    if (g_bank.n_mels == n_mels && g_bank_key[0] == sample_rate && g_bank_key[1] == f_min && g_bank_key[2] == f_max) {
+        *out = g_bank;
         return B200X_OK;
+    }
     std::vector<double> f_pts(n_mels + 2);
     const double m_min = 2595.0 * std::log10(1.0 + f_min / 700.0), m_max = 2595.0 * std::log10(1.0 + f_max / 700.0);
     for (int i = 0; i < n_mels + 2; ++i) {
@@ -835,6 +841,7 @@ static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_ma
     B200X_CUDA_TRY(cudaMemcpy(g_bank.d_seg_weights, w.data(), NBIN * sizeof(float2), cudaMemcpyHostToDevice));
     g_bank.n_mels = n_mels;
     g_bank_key[0] = sample_rate; g_bank_key[1] = f_min; g_bank_key[2] = f_max;
+    *out = g_bank;
     return B200X_OK;
 }
 }  // namespace b200x
@@ -865,9 +872,9 @@ extern "C" int b200x_mel_db_ref(const float* d_y, int64_t y_stride, int64_t n_sa
     B200X_REQUIRE(n_samples > NFFT / 2 && copies > 0, "mel: bad sizes");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     B200X_TRY(ensure_tables(s));
-    B200X_TRY(ensure_melbank(sample_rate, n_mels, f_min, f_max));
-    static bool cfg = false;
-    if (!cfg) { B200X_CUDA_TRY(cudaFuncSetAttribute(mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEL_SMEM)); cfg = true; }
+    MelBank g_bank;
+    B200X_TRY(ensure_melbank(sample_rate, n_mels, f_min, f_max, &g_bank));
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(mel_db_kernel), MEL_SMEM));
     MelParams p;
     p.y = d_y; p.y_stride = y_stride; p.n_samples = n_samples; p.sumsq = d_sumsq; p.ref_rms = ref_rms; p.ref_rms_arr = d_ref_rms_per_copy; p.rms_count = rms_count;
     p.n_frames = 1 + static_cast<int>(n_samples / HOP); p.n_mels = n_mels;

@@ -58,6 +58,7 @@ int pick_block_n(int n, int k = 1 << 30) {
 
 struct b200x_engine {
     b200x_model_config cfg;
+    int device = 0;            // the CUDA device this engine lives on (made current by every entry point)
     int C = 0;                 // copies per chunk
     int64_t max_samples = 0;
     int T = 0, Tt = 0, Ts = 0; // tokens total / temporal / spectral
@@ -99,8 +100,10 @@ struct b200x_engine {
     // CUDA graphs of the classifier forward, one per chunk shape: the ~90 launches of a chunk are replayed with one
     // cudaGraphLaunch (inter-kernel gaps shrink, no host work per kernel).  state 0 = unseen (run eagerly once: lazy
     // one-time initialisation must not happen inside a capture), 1 = warmed (capture on the next use), 2 = ready.
-    struct ChunkGraph { int state = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+    struct ChunkGraph { int state = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t last_use = 0; };
     std::map<std::tuple<int, int64_t, int, int>, ChunkGraph> graphs;
+    uint64_t graph_clock = 0;
+    static constexpr size_t max_graphs = 16;   // least-recently-used shapes beyond this are destroyed (tracks of many lengths)
     bool use_graphs = true;
     DevBuf prob_chunk, logit_chunk, ranges_chunk;      // fixed addresses baked into the graphs
 
@@ -183,46 +186,42 @@ int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const dou
     // tokenizers: temporal rows = t_clip consecutive time steps x n_mels; spectral rows = one mel row over time
     const int Kt = c.t_clip * c.input_spec_dim;
     TIMED(KC_GEMM, b200x_gemm_bf16(e->img_t.p, Kt, e->tok_t_w.p, Kt, copies * e->Tt, D, Kt, pick_block_n(D), e->x.p, D,
-                              B200X_GEMM_OUT_F32_TOKEN, e->tok_t_b.as<float>(), 1, nullptr, e->pe_t.as<float>(), e->Tt, T, 0, s));
+                              B200X_GEMM_OUT_F32_TOKEN, e->tok_t_b.as<float>(), 1, nullptr, e->pe_t.as<float>(), e->Tt, T, 0, 0, s));
     TIMED(KC_GEMM, b200x_gemm_bf16(e->img_f.p, c.input_temp_dim, e->tok_s_w.p, c.input_temp_dim, copies * e->Ts, D,
                               c.input_temp_dim, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_TOKEN, e->tok_s_b.as<float>(), 1,
-                              nullptr, e->pe_s.as<float>(), e->Ts, T, e->Tt, s));
+                              nullptr, e->pe_s.as<float>(), e->Ts, T, e->Tt, 0, s));
     e->launches += 2;
     if (c.pre_norm) {
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, e->np_t_g.as<float>(), e->np_t_b.as<float>(), e->np_s_g.as<float>(),
-                                  e->np_s_b.as<float>(), T, e->Tt, c.tokenizer_ln_eps, nullptr, e->x.as<float>(), s));
+                                  e->np_s_b.as<float>(), T, e->Tt, c.tokenizer_ln_eps, nullptr, e->x.as<float>(), 0, s));
         e->launches += 1;
     }
     const size_t xbytes = static_cast<size_t>(M) * D * sizeof(float);
     if (e->trace) B200X_CUDA_TRY(cudaMemcpyAsync(e->trace, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
+    // Alternating traversal: consecutive kernels of the forward walk their rows / tiles / (copy, head) blocks in opposite
+    // directions, so each one starts on the part of its input that its producer wrote last and that is still in L2 (the
+    // 229-copy activations are 0.25-1.1 GB per tensor).  The direction is a launch ARGUMENT (no process-wide state).
     int rev = 1;                          // the first LayerNorm walks forward (rev flips to 0 before its launch)
+    auto dir = [&]() { if (e->alternate) rev ^= 1; else rev = 0; return rev; };
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
-        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n1_g.as<float>(), w.n1_b.as<float>(), nullptr, nullptr, 0, 0,
-                                  c.block_ln_eps, e->h.p, nullptr, s));
-        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
+                                  c.block_ln_eps, e->h.p, nullptr, dir(), s));
         TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D, D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
-                                  c.qkv_bias ? w.qkv_b.as<float>() : nullptr, 0, nullptr, nullptr, 0, 0, 0, s));
-        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
-        TIMED(KC_ATTN, b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, s));
-        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
+                                  c.qkv_bias ? w.qkv_b.as<float>() : nullptr, 0, nullptr, nullptr, 0, 0, 0, dir(), s));
+        TIMED(KC_ATTN, b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, dir(), s));
         TIMED(KC_GEMM, b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D, D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
-                                  w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
-        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
+                                  w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, dir(), s));
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
-                                  c.block_ln_eps, e->h.p, nullptr, s));
-        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
+                                  c.block_ln_eps, e->h.p, nullptr, dir(), s));
         TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp, D), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
-                                  w.fc1_b.as<float>(), 1, nullptr, nullptr, 0, 0, 0, s));
-        if (e->alternate) { rev ^= 1; b200x_set_traversal(rev); }
+                                  w.fc1_b.as<float>(), 1, nullptr, nullptr, 0, 0, 0, dir(), s));
         TIMED(KC_GEMM, b200x_gemm_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, pick_block_n(D), e->x.p, D,
-                                  B200X_GEMM_OUT_F32_RESID, w.fc2_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, s));
+                                  B200X_GEMM_OUT_F32_RESID, w.fc2_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, dir(), s));
         e->launches += 7;
         if (e->trace)
             B200X_CUDA_TRY(cudaMemcpyAsync(e->trace + static_cast<size_t>(l + 1) * M * D, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
     }
-    b200x_set_traversal(0);
     TIMED(KC_HEAD, b200x_head(e->x.as<float>(), copies, T, D, e->fn_g.as<float>(), e->fn_b.as<float>(), c.block_ln_eps, c.final_norm,
                          e->cls_w.as<float>(), e->cls_b, e->head_part.as<float>(), d_logit, d_prob, s));
     e->launches += 2;
@@ -241,7 +240,19 @@ int forward_chunk(b200x_engine* e, int copies, int64_t n_samples, const double* 
     const int32_t* g_ranges = d_ranges ? e->ranges_chunk.as<int32_t>() : nullptr;
     float* g_prob = e->prob_chunk.as<float>();
     float* g_logit = e->logit_chunk.as<float>();
-    b200x_engine::ChunkGraph& g = e->graphs[std::make_tuple(copies, n_samples, d_ranges ? 1 : 0, max_range)];
+    const auto key = std::make_tuple(copies, n_samples, d_ranges ? 1 : 0, max_range);
+    if (e->graphs.find(key) == e->graphs.end() && e->graphs.size() >= b200x_engine::max_graphs) {
+        auto victim = e->graphs.begin();                  // evict the least recently used shape
+        for (auto it = e->graphs.begin(); it != e->graphs.end(); ++it)
+            if (it->second.last_use < victim->second.last_use) victim = it;
+        if (victim->second.exec) {
+            B200X_CUDA_TRY(cudaStreamSynchronize(s));     // the victim may still be executing
+            cudaGraphExecDestroy(victim->second.exec);
+        }
+        e->graphs.erase(victim);
+    }
+    b200x_engine::ChunkGraph& g = e->graphs[key];
+    g.last_use = ++e->graph_clock;
     if (g.state == 0) {
         B200X_TRY(forward_chunk_body(e, copies, n_samples, nullptr, 0, g_prob, g_logit, g_ranges, max_range));
         g.state = 1;
@@ -285,6 +296,7 @@ int ensure_ref_rms(b200x_engine* e) {
 
 int check_ready(b200x_engine* e, bool need_track) {
     if (e == nullptr) return set_error(B200X_ERR_INVALID, "engine is NULL");
+    B200X_CUDA_TRY(cudaSetDevice(e->device));         // several engines (one per GPU) may share a host thread
     if (!e->finalized) return set_error(B200X_ERR_STATE, "engine weights not finalized");
     if (need_track && e->L == 0) return set_error(B200X_ERR_STATE, "no track loaded (call b200x_engine_set_track)");
     return B200X_OK;
@@ -313,6 +325,7 @@ extern "C" int b200x_engine_create(const b200x_model_config* cfg, int copies_per
     B200X_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     B200X_REQUIRE(major == 10, "engine: this library contains sm_100a code only (device has compute capability %d.x)", major);
     b200x_engine* e = new b200x_engine();
+    e->device = dev;
     e->cfg = *cfg;
     e->C = copies_per_chunk;
     e->max_samples = max_samples;
@@ -361,6 +374,7 @@ extern "C" int b200x_engine_create(const b200x_model_config* cfg, int copies_per
 
 extern "C" void b200x_engine_destroy(b200x_engine* e) {
     if (!e) return;
+    cudaSetDevice(e->device);
     for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     e->graphs.clear();
     DevBuf* bufs[] = {&e->tok_t_w, &e->tok_s_w, &e->tok_t_b, &e->tok_s_b, &e->pe_t, &e->pe_s, &e->np_t_g, &e->np_t_b, &e->np_s_g,
@@ -385,6 +399,7 @@ extern "C" int b200x_engine_set_param(b200x_engine* e, const char* name, const f
 
 extern "C" int b200x_engine_finalize(b200x_engine* e) {
     B200X_REQUIRE(e != nullptr, "finalize: engine is NULL");
+    B200X_CUDA_TRY(cudaSetDevice(e->device));
     const b200x_model_config& c = e->cfg;
     const int D = e->D, F = c.input_spec_dim, Tm = c.input_temp_dim, H = c.mlp_hidden, Hp = e->Hp;
     const std::vector<float>* p = nullptr;
@@ -994,6 +1009,7 @@ extern "C" int b200x_engine_band_map(b200x_engine* e, const int32_t* band_rows, 
 
 extern "C" int b200x_engine_rank(b200x_engine* e, const double* values, int n, int mode, int32_t* order_host) {
     B200X_REQUIRE(e != nullptr, "rank: engine is NULL");
+    B200X_CUDA_TRY(cudaSetDevice(e->device));
     if (n == 0) return B200X_OK;
     B200X_REQUIRE(values && order_host && n > 0, "rank: bad argument");
     B200X_TRY(ensure_grow(e->delta, static_cast<size_t>(n) * sizeof(double)));

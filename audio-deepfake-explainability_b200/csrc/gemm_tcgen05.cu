@@ -519,24 +519,15 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
 }
 
-static int g_num_sms = 0;
-
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
                        const GemmParams& p, cudaStream_t stream) {
     using L = GemmSmem<BN>;
-    static bool configured = false;
-    if (!configured) {
-        B200X_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        configured = true;
-    }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        B200X_CUDA_TRY(cudaGetDevice(&dev));
-        B200X_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int num_sms = 0;
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(gemm_bf16_tn_kernel<BN>), L::TOTAL));
+    B200X_TRY(device_sm_count(&num_sms));
     const int tiles = ceil_div(p.M, GEMM_BM) * ceil_div(p.N, BN);
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    const int grid = tiles < num_sms ? tiles : num_sms;
     gemm_bf16_tn_kernel<BN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmCtail, p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
@@ -546,18 +537,11 @@ template <int BN>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
                         const GemmParams& p, cudaStream_t stream) {
     using L = Gemm2Smem<BN>;
-    static bool configured = false;
-    if (!configured) {
-        B200X_CUDA_TRY(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        configured = true;
-    }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        B200X_CUDA_TRY(cudaGetDevice(&dev));
-        B200X_CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int num_sms = 0;
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(gemm2_bf16_tn_kernel<BN>), L::TOTAL));
+    B200X_TRY(device_sm_count(&num_sms));
     const int tiles = ceil_div(p.M, 2 * GEMM_BM) * ceil_div(p.N, BN);
-    const int pairs = std::min(tiles, g_num_sms / 2);
+    const int pairs = std::min(tiles, num_sms / 2);
     gemm2_bf16_tn_kernel<BN><<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmCtail, p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
@@ -567,18 +551,10 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 
 using namespace b200x;
 
-static int g_gemm_pair = 1;
-// diagnostic only: 0 forces the single-CTA kernel for every problem
-extern "C" void b200x_debug_gemm_pair(int on) { g_gemm_pair = on; }
-
-static long long* g_gemm_prof = nullptr;
-// diagnostic only (not part of the public header): device buffer of 4 long long per CTA for the issuer's cycle counters
-extern "C" void b200x_debug_gemm_profile(void* d_buf) { g_gemm_prof = static_cast<long long*>(d_buf); }
-
 extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n,
                                void* d_out, int ldc, int out_mode, const float* d_bias, int act_gelu,
                                const float* d_resid, const float* d_pe, int group_in, int group_out, int group_off,
-                               void* stream) {
+                               int reverse, void* stream) {
     B200X_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B200X_REQUIRE(N % 16 == 0, "gemm: N=%d must be a multiple of 16", N);
     B200X_REQUIRE(d_bias == nullptr || (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0, "gemm: bias not 16-byte aligned");
@@ -597,7 +573,7 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
     const uint64_t dw[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t sw[1] = {static_cast<uint64_t>(ldw) * 2};
     // CTA-pair kernel (256 x BN tiles, each CTA loads half of the B tile) for everything but the token epilogue
-    const bool pair = g_gemm_pair && out_mode != B200X_GEMM_OUT_F32_TOKEN && block_n != 128 && M > GEMM_BM;
+    const bool pair = out_mode != B200X_GEMM_OUT_F32_TOKEN && block_n != 128 && M > GEMM_BM;
     const uint32_t bw[2] = {GEMM_BK, static_cast<uint32_t>(pair ? block_n / 2 : block_n)};
     B200X_TRY(make_tmap_bf16(&tmB, d_w, 2, dw, sw, bw));
     // output maps: 32-row slabs, 128 bytes wide (64 bf16 / 32 fp32), plus a dense 16-column bf16 tail map
@@ -616,7 +592,7 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
         tmC = tmA;            // unused in token mode
         tmCtail = tmA;
     }
-    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off, g_gemm_prof, pair ? g_traverse_reverse : 0};
+    GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off, nullptr, (pair && reverse) ? 1 : 0};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (pair) {
         switch (block_n) {

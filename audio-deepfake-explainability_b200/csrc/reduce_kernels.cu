@@ -200,19 +200,24 @@ __global__ void delta_kernel(const float* __restrict__ prob, float baseline, int
     if (i < n) delta[i] = static_cast<double>(baseline) - static_cast<double>(prob[i]);
 }
 
+__global__ void delta_dev_kernel(const float* __restrict__ prob, const float* __restrict__ baseline, int n, double* __restrict__ delta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) delta[i] = static_cast<double>(__ldg(baseline)) - static_cast<double>(prob[i]);
+}
+
 }  // namespace b200x
 
 using namespace b200x;
 
 extern "C" int b200x_layernorm(const float* d_x, int rows, int dim, const float* d_gamma, const float* d_beta,
                                const float* d_gamma2, const float* d_beta2, int group, int split, float eps,
-                               void* d_out_bf16, float* d_out_f32, void* stream) {
+                               void* d_out_bf16, float* d_out_f32, int reverse, void* stream) {
     B200X_REQUIRE(rows > 0 && dim % 128 == 0 && dim <= 1024, "layernorm: dim=%d must be a multiple of 128 (<= 1024)", dim);
     B200X_REQUIRE((d_out_bf16 != nullptr) != (d_out_f32 != nullptr), "layernorm: exactly one output");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = ceil_div(rows, 8);
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(d_out_bf16);
-#define LN_CASE(V) case V: layernorm_kernel<V><<<grid, 256, 0, s>>>(d_x, rows, dim, d_gamma, d_beta, d_gamma2 ? d_gamma2 : d_gamma, d_beta2 ? d_beta2 : d_beta, group, split, eps, ob, d_out_f32, g_traverse_reverse); break;
+#define LN_CASE(V) case V: layernorm_kernel<V><<<grid, 256, 0, s>>>(d_x, rows, dim, d_gamma, d_beta, d_gamma2 ? d_gamma2 : d_gamma, d_beta2 ? d_beta2 : d_beta, group, split, eps, ob, d_out_f32, reverse != 0); break;
     switch (dim / 128) { LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
         default: return set_error(B200X_ERR_INVALID, "layernorm: dim=%d not instantiated", dim); }
 #undef LN_CASE
@@ -238,6 +243,14 @@ extern "C" int b200x_head(const float* d_x, int copies, int tokens, int dim, con
 }
 
 extern "C" int b200x_head_slices(void) { return 8; }
+
+extern "C" int b200x_delta_dev(const float* d_prob, const float* d_baseline, int n, double* d_delta, void* stream) {
+    if (n <= 0) return B200X_OK;
+    B200X_REQUIRE(d_prob && d_baseline && d_delta, "delta_dev: NULL argument");
+    delta_dev_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_prob, d_baseline, n, d_delta);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
 
 extern "C" int b200x_delta(const float* d_prob, float baseline, int n, double* d_delta, void* stream) {
     if (n <= 0) return B200X_OK;

@@ -2,8 +2,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <set>
 #include <unordered_map>
+#include <utility>
 
 #include "common.h"
 
@@ -11,10 +14,43 @@ namespace b200x {
 
 static thread_local char g_err[1024] = "";
 
-// Traversal direction of the NEXT launches of the row / tile-ordered kernels (LayerNorm, GEMM, attention).  The engine flips
-// it between consecutive kernels of the forward: a kernel that walks its rows in the opposite order of its producer starts
-// on the ~100 MB the producer wrote last, which are still in L2 (the 228-copy activations are 0.25-1.1 GB per tensor).
-int g_traverse_reverse = 0;
+// ---- per-device one-time state ----------------------------------------------------------------------------------------
+static std::mutex g_dev_mutex;
+static std::set<std::pair<int, const void*>> g_dev_done;       // (device, key) pairs already initialised / configured
+static std::map<int, int> g_dev_sms;
+
+int device_first_use(const void* key, bool* first) {
+    int dev = 0;
+    B200X_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    *first = g_dev_done.insert(std::make_pair(dev, key)).second;
+    return B200X_OK;
+}
+
+int ensure_kernel_smem(const void* func, int bytes, bool max_carveout) {
+    int dev = 0;
+    B200X_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_dev_mutex);             // held across the attribute calls: a second thread must not launch early
+    if (g_dev_done.count(std::make_pair(dev, func))) return B200X_OK;
+    B200X_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (max_carveout) B200X_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    g_dev_done.insert(std::make_pair(dev, func));
+    return B200X_OK;
+}
+
+int device_sm_count(int* sms) {
+    int dev = 0;
+    B200X_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    auto it = g_dev_sms.find(dev);
+    if (it == g_dev_sms.end()) {
+        int n = 0;
+        B200X_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        it = g_dev_sms.emplace(dev, n).first;
+    }
+    *sms = it->second;
+    return B200X_OK;
+}
 
 int set_error(int code, const char* fmt, ...) {
     va_list ap;
@@ -115,5 +151,3 @@ extern "C" int b200x_device_count(int* count) {
     B200X_CUDA_TRY(cudaGetDeviceCount(count));
     return B200X_OK;
 }
-
-extern "C" void b200x_set_traversal(int reverse) { b200x::g_traverse_reverse = reverse != 0; }

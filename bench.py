@@ -742,6 +742,13 @@ def run_engine(args):
                              "parity of the port's DSP / classifier modules is unpinned (librosa / sonics absent from the image)"}
         line["cpu_baseline"] = cpu
         emit(line)
+    # every torch tensor that was used on the engine's stream must be released BEFORE the engine destroys that stream
+    # (the caching allocator records an event on each stream a block was used on when the block is freed)
+    weak = None
+    import gc
+    gc.collect()
+    ctx.torch.cuda.synchronize()
+    ctx.torch.cuda.empty_cache()
     ctx.close()
 
 
@@ -780,6 +787,9 @@ def main():
         run_reference(args)
     else:
         run_engine(args)
+    _RESULT_OUT.flush()
+    sys.stderr.flush()
+    os._exit(0)       # the line is out and every rank has left its last barrier: skip interpreter teardown (NCCL / CUDA atexit order)
 
 
 if __name__ == "__main__":

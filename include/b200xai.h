@@ -121,22 +121,23 @@ int b200x_mix_stems(const float* d_stems, int64_t n_samples, int n_stems, const 
  * SpecTTTra forward. */
 int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n, void* d_out,
                     int ldc, int out_mode, const float* d_bias, int act_gelu, const float* d_resid, const float* d_pe,
-                    int group_in, int group_out, int group_off, void* stream);
+                    int group_in, int group_out, int group_off, int reverse, void* stream);
 
 /* fused softmax(Q K^T / sqrt(d)) V for d_qkv bf16 [copies*tokens][3*heads*64] = [q|k|v]; d_out bf16
  * [copies*tokens][heads*64].  (F.scaled_dot_product_attention inside the third-party encoder) */
-int b200x_attention(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int head_dim, void* stream);
+int b200x_attention(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int head_dim, int reverse,
+                    void* stream);
 
-/* Traversal direction of the following LayerNorm / GEMM (CTA-pair kernel) / attention launches: reverse != 0 walks rows,
- * tiles and (copy, head) blocks from the end.  Results do not depend on it; the engine alternates it between consecutive
- * kernels so that each one starts on the part of its input that the previous kernel wrote last and that is still in L2. */
-void b200x_set_traversal(int reverse);
+/* `reverse` (GEMM CTA-pair kernel, attention, LayerNorm): != 0 walks tiles, (copy, head) blocks and rows from the end.
+ * Results do not depend on it; the engine alternates it between consecutive kernels of the forward so that each one starts
+ * on the part of its input that the previous kernel wrote last and that is still in L2.  It is a per-launch argument:
+ * the library keeps no process-wide mutable state (engines on several GPUs / host threads do not interact). */
 
 /* LayerNorm over dim (fp32 in); rows with (row % group) >= split use (gamma2, beta2) when group > 0.
  * Exactly one of d_out_bf16 / d_out_f32 (may alias d_x) is non-NULL. */
 int b200x_layernorm(const float* d_x, int rows, int dim, const float* d_gamma, const float* d_beta,
                     const float* d_gamma2, const float* d_beta2, int group, int split, float eps, void* d_out_bf16,
-                    float* d_out_f32, void* stream);
+                    float* d_out_f32, int reverse, void* stream);
 
 /* final LayerNorm (optional) + token mean + Linear(dim,1) + sigmoid.  d_partial: copies*b200x_head_slices() floats. */
 int b200x_head_slices(void);
@@ -146,6 +147,8 @@ int b200x_head(const float* d_x, int copies, int tokens, int dim, const float* d
 
 /* delta[i] = (double)baseline - (double)prob[i]      (importance = baseline_pred - occluded_pred, :684) */
 int b200x_delta(const float* d_prob, float baseline, int n, double* d_delta, void* stream);
+/* same with the baseline read from device memory (no host round trip between the sweep and the reductions) */
+int b200x_delta_dev(const float* d_prob, const float* d_baseline, int n, double* d_delta, void* stream);
 
 /* importance map: map[f0:f1,t0:t1] += delta; count += 1; map /= count + 1e-8  (float64 [n_freq][n_time], window order;
  * src/spectrogram_explainability.py:695-696, 707) */
@@ -166,7 +169,8 @@ int b200x_band_map(const int32_t* d_band_rows, const double* d_delta, int n_band
 int b200x_rank(const double* d_values, int n, int mode, int32_t* d_order, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Engine-level entry points (host or device buffers; one engine per GPU / process; not re-entrant per engine)
+ * Engine-level entry points (host or device buffers; an engine belongs to the CUDA device that was current at creation and
+ * makes it current in every call; engines on different GPUs may coexist in one process; not re-entrant per engine)
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct b200x_engine b200x_engine;
 
@@ -253,8 +257,8 @@ int64_t b200x_engine_launch_count(b200x_engine* e);
 /* per-kernel-class CUDA-event timing on the engine stream: classes 0 istft, 1 mel, 2 normalise/resize, 3 gemm,
  * 4 attention, 5 layernorm, 6 head, 7 other; get_timing returns the sums since set_timing / the last get (8 entries). */
 int b200x_engine_set_timing(b200x_engine* e, int enable);
-/* Alternate the traversal direction between consecutive kernels of the classifier forward (default on; see
- * b200x_set_traversal).  Results are unaffected. */
+/* Alternate the traversal direction between consecutive kernels of the classifier forward (default on; see the `reverse`
+ * launch argument above).  Results are unaffected. */
 int b200x_engine_set_alternate(b200x_engine* e, int enable);
 /* The classifier forward of a chunk is replayed from a CUDA graph once its shape has been seen twice (default on);
  * 0 = always launch kernel by kernel.  Results are identical either way. */

@@ -16,11 +16,11 @@ def test_layernorm_bf16_and_inplace_groups():
     ga, ba = torch.randn(384, generator=g), torch.randn(384, generator=g)
     gb, bb = torch.randn(384, generator=g), torch.randn(384, generator=g)
     out = torch.zeros(x.shape, dtype=torch.bfloat16, device="cuda")
-    ok(lib().b200x_layernorm(P(D(x)), x.shape[0], 384, P(D(ga)), P(D(ba)), P(None), P(None), 0, 0, 1e-5, P(out), P(None), P(None)))
+    ok(lib().b200x_layernorm(P(D(x)), x.shape[0], 384, P(D(ga)), P(D(ba)), P(None), P(None), 0, 0, 1e-5, P(out), P(None), 0, P(None)))
     ref = torch.nn.functional.layer_norm(x, (384,), ga, ba, 1e-5)
     assert (out.float().cpu() - ref).abs().max().item() < 8e-3 * ref.abs().max().item()   # bf16 output: 2^-8 relative
     xi = x[: 2 * 1376].cuda().clone()
-    ok(lib().b200x_layernorm(P(xi), 2 * 1376, 384, P(D(ga)), P(D(ba)), P(D(gb)), P(D(bb)), 1376, 1248, 1e-6, P(None), P(xi), P(None)))
+    ok(lib().b200x_layernorm(P(xi), 2 * 1376, 384, P(D(ga)), P(D(ba)), P(D(gb)), P(D(bb)), 1376, 1248, 1e-6, P(None), P(xi), 0, P(None)))
     xr = x[: 2 * 1376].reshape(2, 1376, 384)
     ref2 = torch.cat([torch.nn.functional.layer_norm(xr[:, :1248], (384,), ga, ba, 1e-6),
                       torch.nn.functional.layer_norm(xr[:, 1248:], (384,), gb, bb, 1e-6)], dim=1).reshape(-1, 384)

@@ -60,21 +60,14 @@ total = 0.0
 
 
 def gemm(a, lda, w, ldw, m, n, k, bn, out, ldc, mode, bias, gelu, resid):
-    _lib.check(lib.b200x_gemm_bf16(P(a), lda, P(w), ldw, m, n, k, bn, P(out), ldc, mode, P(bias), gelu, P(resid), P(None), 0, 0, 0, P(None)))
+    _lib.check(lib.b200x_gemm_bf16(P(a), lda, P(w), ldw, m, n, k, bn, P(out), ldc, mode, P(bias), gelu, P(resid), P(None), 0, 0, 0, 0, P(None)))
 
 
 print(f"copies={copies}  M={M}")
-if os.environ.get("KB_ATTN_VARIANTS"):
-    import ctypes
-    lib.b200x_debug_attention_tiles_per_cta(ctypes.c_int(int(os.environ.get('KB_ATTN_NQ', '2'))))
-    for v in [int(t) for t in os.environ.get('KB_ATTN_LIST', '0,1,4,12,20,28').split(',')]:
-        lib.b200x_debug_attention_variant(ctypes.c_int(v))
-        timeit(lambda: _lib.check(lib.b200x_attention(P(qkv), P(att), copies, T, H, 64, P(None))), flops=4 * copies * H * T * T * 64, name=f"attention variant {v}")
-    sys.exit(0)
-total += timeit(lambda: _lib.check(lib.b200x_layernorm(P(x), M, D, P(gam), P(bet), P(None), P(None), 0, 0, 1e-5, P(h), P(None), P(None))),
+total += timeit(lambda: _lib.check(lib.b200x_layernorm(P(x), M, D, P(gam), P(bet), P(None), P(None), 0, 0, 1e-5, P(h), P(None), 0, P(None))),
                 bytes_=M * D * 6, name="layernorm fp32->bf16") * 2
 total += timeit(lambda: gemm(h, D, w_qkv, D, M, 3 * D, D, 192, qkv, 3 * D, 0, None, 0, None), flops=2 * M * D * 3 * D, name="gemm qkv   N=1152 K=384  bf16")
-total += timeit(lambda: _lib.check(lib.b200x_attention(P(qkv), P(att), copies, T, H, 64, P(None))), flops=4 * copies * H * T * T * 64, name="attention")
+total += timeit(lambda: _lib.check(lib.b200x_attention(P(qkv), P(att), copies, T, H, 64, 0, P(None))), flops=4 * copies * H * T * T * 64, name="attention")
 total += timeit(lambda: gemm(att, D, w_proj, D, M, D, D, 192, x, D, 1, b_d, 0, x), flops=2 * M * D * D, name="gemm proj  N=384  K=384  resid")
 total += timeit(lambda: gemm(h, D, w_fc1, D, M, HP, D, 208, hid, HP, 0, b_h, 1, None), flops=2 * M * D * HP, name="gemm fc1   N=1040 K=384  gelu")
 total += timeit(lambda: gemm(hid, HP, w_fc2, HP, M, D, HP, 192, x, D, 1, b_d, 0, x), flops=2 * M * D * HP, name="gemm fc2   N=384  K=1040 resid")
