@@ -61,6 +61,18 @@ SIGNATURES = {
     "b200x_mel_db_ref": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, VP, C.c_double, VP,
                                     C.c_int64, VP, C.c_int, VP, VP, C.c_int, VP]),
     "b200x_wave_rms": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int, C.c_int, VP, VP]),
+    "b200x_stft_batch": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int, VP, C.c_int, C.c_int64, VP]),
+    "b200x_mel_power": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP]),
+    "b200x_mel_nnls": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_float, VP, VP, VP, VP, VP, VP, C.c_float, C.c_int, VP, C.c_int,
+                                 VP, C.c_int64, VP]),
+    "b200x_gl_init": (C.c_int, [VP, C.c_int64, VP, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int, VP]),
+    "b200x_gl_update": (C.c_int, [VP, VP, VP, C.c_int64, VP, C.c_int64, C.c_int, C.c_int, C.c_float, VP]),
+    "b200x_engine_saliency_map_shape": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]),
+    "b200x_engine_set_mel_basis": (C.c_int, [VP, C.c_int, VP, VP, C.c_float]),
+    "b200x_engine_mel_spectrogram": (C.c_int, [VP, VP]),
+    "b200x_engine_mel_sweep": (C.c_int, [VP, C.c_int, VP, VP, C.c_int, C.c_float, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_float, VP, VP]),
+    "b200x_resample_poly": (C.c_int, [VP, C.c_int64, C.c_int, C.c_int, VP, C.c_int, VP, C.c_int64, VP]),
+    "b200x_engine_resample": (C.c_int, [VP, VP, C.c_int64, C.c_int, C.c_int, VP, C.c_int, VP, C.c_int64]),
     "b200x_rise_map": (C.c_int, [VP, C.c_int, C.c_uint32, C.c_double, C.c_int, C.c_int, VP, VP]),
     "b200x_band_map": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, VP, VP]),
     "b200x_rank": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),

@@ -87,10 +87,12 @@ __device__ __forceinline__ void rfft_unpack(const float2 (&v)[32], float2* tile,
 
 // ------------------------------------------------------------------------------------------------ STFT (librosa)
 __global__ void __launch_bounds__(DSP_THREADS)
-stft_kernel(const float* __restrict__ y, long long n_samples, int n_frames, int reflect, float2* __restrict__ S,
-            int stride) {
+stft_kernel(const float* __restrict__ y_all, long long n_samples, int n_frames, int reflect, float2* __restrict__ S_all,
+            int stride, long long y_copy_stride, long long s_copy_stride) {
     extern __shared__ __align__(16) float2 dsp_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* __restrict__ y = y_all + static_cast<long long>(blockIdx.y) * y_copy_stride;        // blockIdx.y = wave of a batch
+    float2* __restrict__ S = S_all + static_cast<long long>(blockIdx.y) * s_copy_stride;
     float2* tile = dsp_smem + warp * FFT_TILE;
     float2* tw = dsp_smem + DSP_WARPS * FFT_TILE;
     fft_fill_twiddles(tw);
@@ -710,7 +712,25 @@ extern "C" int b200x_stft(const float* d_wave, int64_t n_samples, int n_fft, int
     B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(stft_kernel), DSP_SMEM));
     const int n_frames = 1 + static_cast<int>(n_samples / HOP);
     const int grid = std::min(ceil_div(n_frames, DSP_WARPS), 148 * 8);
-    stft_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(d_wave, n_samples, n_frames, reflect_pad, reinterpret_cast<float2*>(d_spec), spec_stride);
+    stft_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(d_wave, n_samples, n_frames, reflect_pad, reinterpret_cast<float2*>(d_spec), spec_stride, 0, 0);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
+// librosa.stft of `copies` equal-length waves in one launch (Griffin-Lim: rebuilt = stft(istft(.)) for a chunk of copies):
+// wave c at d_waves + c * wave_stride floats, spectrum c at d_spec + c * spec_copy_stride complex values
+extern "C" int b200x_stft_batch(const float* d_waves, int64_t n_samples, int64_t wave_stride, int copies, void* d_spec,
+                                int spec_stride, int64_t spec_copy_stride, void* stream) {
+    B200X_REQUIRE(d_waves && d_spec && copies > 0, "stft_batch: bad argument");
+    B200X_REQUIRE(n_samples > NFFT / 2 && spec_stride >= NBIN && wave_stride >= n_samples, "stft_batch: bad sizes");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    B200X_TRY(ensure_tables(s));
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(stft_kernel), DSP_SMEM));
+    const int n_frames = 1 + static_cast<int>(n_samples / HOP);
+    B200X_REQUIRE(spec_copy_stride >= static_cast<int64_t>(n_frames) * spec_stride, "stft_batch: spec_copy_stride too small");
+    dim3 grid(std::min(ceil_div(n_frames, DSP_WARPS), 148 * 8), copies);
+    stft_kernel<<<grid, DSP_THREADS, DSP_SMEM, s>>>(d_waves, n_samples, n_frames, 0, reinterpret_cast<float2*>(d_spec), spec_stride, wave_stride,
+                                                    spec_copy_stride);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }

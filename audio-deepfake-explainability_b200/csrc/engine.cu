@@ -97,6 +97,16 @@ struct b200x_engine {
     int last_copies = 0;
     float* trace = nullptr;
 
+    // mel-domain explainer variant (spec_type: mel): Slaney filterbank operators, the track's power mel spectrogram, the
+    // baseline NNLS magnitude and the Griffin-Lim workspace of one chunk of copies (allocated on first use)
+    int mel_n = 0;             // n_mels of the uploaded basis (0 = none)
+    float mel_step = 0.f;
+    DevBuf mel_basis, mel_bin_range, mel_bin_first, mel_bin_w, mel_pinv_t, mel_track, mel_mag_base, mel_frames;
+    DevBuf gl_mag, gl_c, gl_r0, gl_r1;
+    int gl_copies = 0;         // copies the Griffin-Lim workspace holds
+    int mel_track_frames = 0;  // n_time the cached mel_track / mel_mag_base belong to (0 = stale)
+    int mel_mag_iter = -1;     // nnls_iter the cached baseline magnitude was solved with
+
     // CUDA graphs of the classifier forward, one per chunk shape: the ~90 launches of a chunk are replayed with one
     // cudaGraphLaunch (inter-kernel gaps shrink, no host work per kernel).  state 0 = unseen (run eagerly once: lazy
     // one-time initialisation must not happen inside a capture), 1 = warmed (capture on the next use), 2 = ready.
@@ -380,7 +390,9 @@ extern "C" void b200x_engine_destroy(b200x_engine* e) {
     DevBuf* bufs[] = {&e->tok_t_w, &e->tok_s_w, &e->tok_t_b, &e->tok_s_b, &e->pe_t, &e->pe_s, &e->np_t_g, &e->np_t_b, &e->np_s_g,
                       &e->np_s_b, &e->fn_g, &e->fn_b, &e->cls_w, &e->wave, &e->S, &e->y, &e->db, &e->cta_max, &e->partial,
                       &e->floor_v, &e->img_t, &e->img_f, &e->x, &e->h, &e->qkv, &e->att, &e->hid, &e->head_part, &e->prob,
-                      &e->logit, &e->sumsq, &e->db_base, &e->base_pre, &e->base_suf, &e->ranges, &e->prob_chunk, &e->logit_chunk, &e->ranges_chunk, &e->windows, &e->gains, &e->masks, &e->stems, &e->delta, &e->order, &e->map};
+                      &e->logit, &e->sumsq, &e->db_base, &e->base_pre, &e->base_suf, &e->ranges, &e->prob_chunk, &e->logit_chunk, &e->ranges_chunk, &e->windows, &e->gains, &e->masks, &e->stems, &e->delta, &e->order, &e->map,
+                      &e->S_multi, &e->ref_arr, &e->mel_basis, &e->mel_bin_range, &e->mel_bin_first, &e->mel_bin_w, &e->mel_pinv_t, &e->mel_track,
+                      &e->mel_mag_base, &e->mel_frames, &e->gl_mag, &e->gl_c, &e->gl_r0, &e->gl_r1};
     for (DevBuf* b : bufs) b->release();
     for (LayerW& w : e->layers) {
         DevBuf* lb[] = {&w.qkv_w, &w.qkv_b, &w.proj_w, &w.proj_b, &w.fc1_w, &w.fc1_b, &w.fc2_w, &w.fc2_b, &w.n1_g, &w.n1_b, &w.n2_g, &w.n2_b};
@@ -532,6 +544,7 @@ extern "C" int b200x_engine_set_track(b200x_engine* e, const float* wave, int64_
     B200X_TRY(b200x_stft(e->wave.as<float>(), n_samples, e->cfg.n_fft, e->cfg.hop_length, 0, e->S.p, b200x_engine::s_stride, e->stream));
     e->launches += 1;
     e->baseline_valid = false;
+    e->mel_track_frames = 0;
     e->ref_rms = -1.0;   // computed lazily (ensure_ref_rms) when a loudness-normalised FBP sweep asks for it
     // the tail of every y row beyond hop*(n_time-1) must read as zero padding (spectrogram_explainability.py:679-680)
     B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, e->y.bytes, e->stream));
@@ -793,6 +806,7 @@ extern "C" int b200x_engine_fbp_sweep_tracks(b200x_engine* e, const float* waves
                                            static_cast<size_t>(track_stride) * 2 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
             e->L = n_samples;
             e->n_time = n_time;
+            e->mel_track_frames = 0;
             e->ref_rms = -1.0;
             // the tail of every y row beyond hop * (n_time - 1) must read as zero padding again for the occlusion path
             B200X_CUDA_TRY(cudaMemsetAsync(e->y.p, 0, e->y.bytes, e->stream));
@@ -1019,6 +1033,234 @@ extern "C" int b200x_engine_rank(b200x_engine* e, const double* values, int n, i
     e->launches += 1;
     B200X_CUDA_TRY(cudaMemcpyAsync(order_host, e->order.p, static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+// Track loader front: resample a decoded track on the device (host buffers in / out; works without weights)
+extern "C" int b200x_engine_resample(b200x_engine* e, const float* x_host, int64_t n_in, int up, int down, const double* h_host,
+                                     int h_len, float* y_host, int64_t n_out) {
+    B200X_REQUIRE(e && x_host && h_host && y_host && n_in > 0 && n_out > 0, "resample: bad argument");
+    B200X_CUDA_TRY(cudaSetDevice(e->device));
+    DevBuf dx, dh, dy;
+    int st = dx.alloc(static_cast<size_t>(n_in) * sizeof(float));
+    if (st == B200X_OK) st = dh.alloc(static_cast<size_t>(h_len) * sizeof(double));
+    if (st == B200X_OK) st = dy.alloc(static_cast<size_t>(n_out) * sizeof(float));
+    auto run = [&]() -> int {
+        B200X_CUDA_TRY(cudaMemcpyAsync(dx.p, x_host, static_cast<size_t>(n_in) * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        B200X_CUDA_TRY(cudaMemcpyAsync(dh.p, h_host, static_cast<size_t>(h_len) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        B200X_TRY(b200x_resample_poly(dx.as<float>(), n_in, up, down, dh.as<double>(), h_len, dy.as<float>(), n_out, e->stream));
+        e->launches += 1;
+        B200X_CUDA_TRY(cudaMemcpyAsync(y_host, dy.p, static_cast<size_t>(n_out) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        return B200X_OK;
+    };
+    if (st == B200X_OK) st = run();
+    dx.release(); dh.release(); dy.release();
+    return st;
+}
+
+// importance map over an arbitrary [n_freq][n_time] grid (the mel variant's map has n_mels rows)
+extern "C" int b200x_engine_saliency_map_shape(b200x_engine* e, const int32_t* windows, const double* delta, int n, int n_freq,
+                                               int n_time, double* map_host) {
+    B200X_TRY(check_ready(e, false));
+    B200X_REQUIRE(map_host && n >= 0 && n_freq > 0 && n_time > 0 && (n == 0 || (windows && delta)), "saliency_map_shape: bad argument");
+    const size_t cells = static_cast<size_t>(n_freq) * n_time;
+    B200X_TRY(ensure_grow(e->map, cells * sizeof(double)));
+    B200X_TRY(ensure_grow(e->windows, static_cast<size_t>(std::max(n, 1)) * 16));
+    B200X_TRY(ensure_grow(e->delta, static_cast<size_t>(std::max(n, 1)) * sizeof(double)));
+    if (n > 0) {
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, windows, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, e->stream));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->delta.p, delta, static_cast<size_t>(n) * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    B200X_TRY(b200x_saliency_reduce(e->windows.as<int32_t>(), e->delta.as<double>(), n, n_freq, n_time, e->map.as<double>(), e->stream));
+    e->launches += 1;
+    B200X_CUDA_TRY(cudaMemcpyAsync(map_host, e->map.p, cells * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return B200X_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- mel-domain variant
+extern "C" int b200x_engine_set_mel_basis(b200x_engine* e, int n_mels, const float* basis, const float* pinv, float step) {
+    B200X_TRY(check_ready(e, false));
+    B200X_REQUIRE(basis && pinv && n_mels > 0 && n_mels <= 1024 && step > 0.f, "set_mel_basis: bad argument");
+    const int F = b200x_engine::n_freq;
+    // sparse structure of the filterbank: the bins of every filter, and the (at most two, adjacent) filters of every bin
+    std::vector<int32_t> bin_range(2 * static_cast<size_t>(n_mels)), bin_first(F, 0);
+    std::vector<float> bin_w(2 * static_cast<size_t>(F), 0.f), pinv_t(static_cast<size_t>(n_mels) * F);
+    for (int i = 0; i < n_mels; ++i) {
+        int lo = F, hi = 0;
+        for (int k = 0; k < F; ++k)
+            if (basis[static_cast<size_t>(i) * F + k] != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k + 1); }
+        if (lo >= hi) { lo = 0; hi = 0; }                // empty filter (narrower than the bin spacing)
+        bin_range[2 * i] = lo; bin_range[2 * i + 1] = hi;
+    }
+    for (int k = 0; k < F; ++k) {
+        int first = -1, count = 0, last = -1;
+        for (int i = 0; i < n_mels; ++i)
+            if (basis[static_cast<size_t>(i) * F + k] != 0.f) { if (first < 0) first = i; last = i; ++count; }
+        B200X_REQUIRE(count <= 2 && (count < 2 || last == first + 1),
+                      "set_mel_basis: bin %d feeds %d filters (%d..%d); triangular filterbanks feed at most two adjacent ones", k, count, first, last);
+        if (first < 0) first = 0;
+        bin_first[k] = first;
+        bin_w[2 * k] = basis[static_cast<size_t>(first) * F + k];
+        bin_w[2 * k + 1] = first + 1 < n_mels ? basis[static_cast<size_t>(first + 1) * F + k] : 0.f;
+    }
+    for (int k = 0; k < F; ++k)
+        for (int i = 0; i < n_mels; ++i) pinv_t[static_cast<size_t>(i) * F + k] = pinv[static_cast<size_t>(k) * n_mels + i];
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    B200X_TRY(upload(e->mel_basis, basis, static_cast<size_t>(n_mels) * F * sizeof(float)));
+    B200X_TRY(upload(e->mel_bin_range, bin_range.data(), bin_range.size() * sizeof(int32_t)));
+    B200X_TRY(upload(e->mel_bin_first, bin_first.data(), bin_first.size() * sizeof(int32_t)));
+    B200X_TRY(upload(e->mel_bin_w, bin_w.data(), bin_w.size() * sizeof(float)));
+    B200X_TRY(upload(e->mel_pinv_t, pinv_t.data(), pinv_t.size() * sizeof(float)));
+    e->mel_n = n_mels;
+    e->mel_step = step;
+    e->mel_track_frames = 0;
+    return B200X_OK;
+}
+
+namespace {
+// power mel spectrogram of the current track (once per track and basis)
+int ensure_mel_track(b200x_engine* e) {
+    B200X_REQUIRE(e->mel_n > 0, "mel: no filterbank uploaded (b200x_engine_set_mel_basis)");
+    if (e->mel_track_frames == e->n_time) return B200X_OK;
+    B200X_TRY(ensure_grow(e->mel_track, static_cast<size_t>(e->n_time) * e->mel_n * sizeof(float)));
+    B200X_TRY(b200x_mel_power(e->S.p, b200x_engine::s_stride, e->n_time, e->mel_n, e->mel_basis.as<float>(), e->mel_bin_range.as<int32_t>(),
+                              e->mel_track.as<float>(), e->stream));
+    e->launches += 1;
+    e->mel_track_frames = e->n_time;
+    e->mel_mag_iter = -1;
+    return B200X_OK;
+}
+
+int nnls_call(b200x_engine* e, int copies, int mode, const int32_t* d_windows, float occ, const float* d_gains, int nnls_iter,
+              const int32_t* d_frames, int max_range, float* d_mag, int64_t mag_copy_stride) {
+    B200X_TRY(b200x_mel_nnls(e->mel_track.as<float>(), e->n_time, e->mel_n, copies, mode, d_windows, occ, d_gains, e->mel_basis.as<float>(),
+                             e->mel_bin_range.as<int32_t>(), e->mel_bin_first.as<int32_t>(), e->mel_bin_w.as<float>(), e->mel_pinv_t.as<float>(),
+                             e->mel_step, nnls_iter, d_frames, max_range, d_mag, mag_copy_stride, e->stream));
+    e->launches += 1;
+    return B200X_OK;
+}
+}  // namespace
+
+extern "C" int b200x_engine_mel_spectrogram(b200x_engine* e, float* mel_host) {
+    B200X_TRY(check_ready(e, true));
+    B200X_REQUIRE(mel_host != nullptr, "mel_spectrogram: NULL output");
+    B200X_TRY(ensure_mel_track(e));
+    std::vector<float> tmp(static_cast<size_t>(e->n_time) * e->mel_n);
+    B200X_CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->mel_track.p, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int t = 0; t < e->n_time; ++t)                       // [frame][mel] on the device -> librosa's [mel][frame]
+        for (int i = 0; i < e->mel_n; ++i) mel_host[static_cast<size_t>(i) * e->n_time + t] = tmp[static_cast<size_t>(t) * e->mel_n + i];
+    return B200X_OK;
+}
+
+// The mel-variant hot loop (src/spectrogram_explainability.py:663-703 with spec_type == 'mel', and the builder's FBP-mel):
+// for every perturbed copy  y = griffinlim(sqrt(nnls(A, perturbed mel))), trimmed / padded to len(track), prob = predict(y).
+// mode: B200X_MASK_OCCLUDE / KEEP_ONLY (windows int32 [n][4] over (frame, mel bin)) or BAND_GAIN (gains float [n][n_mels]).
+// Copy i starts Griffin-Lim from the phases of index first_index + i.  audio_host (nullable): float [n][hop * (n_time - 1)].
+extern "C" int b200x_engine_mel_sweep(b200x_engine* e, int mode, const int32_t* windows, const float* gains, int n, float occlusion_value,
+                                      int n_iter, int nnls_iter, uint32_t seed, int first_index, float momentum, float* prob,
+                                      float* audio_host) {
+    B200X_TRY(check_ready(e, true));
+    if (n == 0) return B200X_OK;
+    B200X_REQUIRE(n > 0 && n_iter >= 0 && nnls_iter >= 0 && first_index >= 0 && (prob || audio_host), "mel_sweep: bad argument");
+    B200X_REQUIRE(mode == B200X_MASK_OCCLUDE || mode == B200X_MASK_KEEP_ONLY || mode == B200X_MASK_BAND_GAIN || mode == B200X_MASK_NONE,
+                  "mel_sweep: bad mode %d", mode);
+    B200X_REQUIRE((mode != B200X_MASK_OCCLUDE && mode != B200X_MASK_KEEP_ONLY) || windows, "mel_sweep: windows missing");
+    B200X_REQUIRE(mode != B200X_MASK_BAND_GAIN || gains, "mel_sweep: gains missing");
+    B200X_TRY(ensure_mel_track(e));
+    const int T = e->n_time, NM = e->mel_n;
+    const int64_t spec_copy = static_cast<int64_t>(T) * b200x_engine::s_stride;      // elements per copy (float or float2)
+    const int64_t out_len = static_cast<int64_t>(e->cfg.hop_length) * (T - 1);
+    const bool window_mode = mode == B200X_MASK_OCCLUDE || mode == B200X_MASK_KEEP_ONLY;
+    // Griffin-Lim workspace: 28 bytes per cell and copy (|STFT|, C, two rebuilt spectra): chunks of at most 16 copies
+    const int G = std::min(std::min(e->C, 16), n);
+    if (e->gl_copies < G) {
+        B200X_TRY(e->gl_mag.alloc(static_cast<size_t>(G) * spec_copy * sizeof(float)));
+        B200X_TRY(e->gl_c.alloc(static_cast<size_t>(G) * spec_copy * 2 * sizeof(float)));
+        B200X_TRY(e->gl_r0.alloc(static_cast<size_t>(G) * spec_copy * 2 * sizeof(float)));
+        B200X_TRY(e->gl_r1.alloc(static_cast<size_t>(G) * spec_copy * 2 * sizeof(float)));
+        e->gl_copies = G;
+    }
+    B200X_TRY(ensure_prob(e, n));
+    std::vector<int32_t> frames(static_cast<size_t>(n) * 2);
+    int max_range = 1;
+    for (int i = 0; i < n; ++i) {
+        int fa = 0, fb = T;
+        if (window_mode) {
+            const int32_t* w = windows + 4 * i;
+            B200X_REQUIRE(w[0] >= 0 && w[0] <= w[1] && w[1] <= T && w[2] >= 0 && w[2] <= w[3] && w[3] <= NM,
+                          "mel_sweep: window %d = (%d,%d,%d,%d) outside the %dx%d mel spectrogram", i, w[0], w[1], w[2], w[3], NM, T);
+            fa = w[0]; fb = w[1];
+        }
+        frames[2 * i] = fa; frames[2 * i + 1] = fb;
+        max_range = std::max(max_range, fb - fa);
+    }
+    B200X_TRY(ensure_grow(e->mel_frames, std::max<size_t>(frames.size(), 2) * sizeof(int32_t)));
+    B200X_CUDA_TRY(cudaMemcpyAsync(e->mel_frames.p, frames.data(), frames.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    if (window_mode) {
+        B200X_TRY(ensure_grow(e->windows, static_cast<size_t>(n) * 16));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->windows.p, windows, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (mode == B200X_MASK_BAND_GAIN) {
+        B200X_TRY(ensure_grow(e->gains, static_cast<size_t>(n) * NM * sizeof(float)));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->gains.p, gains, static_cast<size_t>(n) * NM * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    }
+    B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));          // `frames` is a stack-lifetime staging buffer
+    // frames outside an occlusion window keep the unperturbed track's NNLS solution (the NNLS is separable per frame)
+    if (mode == B200X_MASK_OCCLUDE && e->mel_mag_iter != nnls_iter) {
+        B200X_TRY(ensure_grow(e->mel_mag_base, static_cast<size_t>(spec_copy) * sizeof(float)));
+        const int32_t all[2] = {0, T};
+        B200X_TRY(ensure_grow(e->ranges, 2 * sizeof(int32_t)));
+        B200X_CUDA_TRY(cudaMemcpyAsync(e->ranges.p, all, sizeof(all), cudaMemcpyHostToDevice, e->stream));
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        B200X_TRY(nnls_call(e, 1, B200X_MASK_NONE, nullptr, 0.f, nullptr, nnls_iter, e->ranges.as<int32_t>(), T, e->mel_mag_base.as<float>(), spec_copy));
+        e->mel_mag_iter = nnls_iter;
+    }
+    const float coef = momentum / (1.0f + momentum);
+    for (int c0 = 0; c0 < n; c0 += G) {
+        const int m = std::min(G, n - c0);
+        float* mag = e->gl_mag.as<float>();
+        if (mode == B200X_MASK_OCCLUDE) {
+            for (int i = 0; i < m; ++i)
+                B200X_CUDA_TRY(cudaMemcpyAsync(mag + static_cast<size_t>(i) * spec_copy, e->mel_mag_base.p, static_cast<size_t>(spec_copy) * sizeof(float),
+                                               cudaMemcpyDeviceToDevice, e->stream));
+        } else if (mode == B200X_MASK_KEEP_ONLY) {
+            B200X_CUDA_TRY(cudaMemsetAsync(mag, 0, static_cast<size_t>(m) * spec_copy * sizeof(float), e->stream));
+        }
+        B200X_TRY(nnls_call(e, m, mode, window_mode ? e->windows.as<int32_t>() + 4 * c0 : nullptr, occlusion_value,
+                            mode == B200X_MASK_BAND_GAIN ? e->gains.as<float>() + static_cast<size_t>(c0) * NM : nullptr, nnls_iter,
+                            e->mel_frames.as<int32_t>() + 2 * c0, max_range, mag, spec_copy));
+        B200X_TRY(b200x_gl_init(mag, spec_copy, e->gl_c.p, spec_copy, m, T, seed, first_index + c0, e->stream));
+        e->launches += 1;
+        for (int it = 0; it < n_iter; ++it) {
+            void* rebuilt = (it & 1) ? e->gl_r1.p : e->gl_r0.p;
+            void* tprev = (it & 1) ? e->gl_r0.p : e->gl_r1.p;
+            TIMED(KC_ISTFT, b200x_istft_masked_tracks(e->gl_c.p, b200x_engine::s_stride, T, m, 1, spec_copy, B200X_MASK_NONE, nullptr, 0.f, nullptr,
+                                                e->y.as<float>(), e->y_stride, nullptr, nullptr, 0, e->stream));
+            TIMED(KC_OTHER, b200x_stft_batch(e->y.as<float>(), out_len, e->y_stride, m, rebuilt, b200x_engine::s_stride, spec_copy, e->stream));
+            TIMED(KC_OTHER, b200x_gl_update(rebuilt, tprev, mag, spec_copy, e->gl_c.p, spec_copy, m, T, it == 0 ? 0.f : coef, e->stream));
+            e->launches += 3;
+        }
+        TIMED(KC_ISTFT, b200x_istft_masked_tracks(e->gl_c.p, b200x_engine::s_stride, T, m, 1, spec_copy, B200X_MASK_NONE, nullptr, 0.f, nullptr,
+                                            e->y.as<float>(), e->y_stride, nullptr, nullptr, 0, e->stream));
+        e->launches += 1;
+        if (audio_host != nullptr)
+            B200X_CUDA_TRY(cudaMemcpy2DAsync(audio_host + static_cast<size_t>(c0) * out_len, out_len * sizeof(float), e->y.p,
+                                             e->y_stride * sizeof(float), out_len * sizeof(float), m, cudaMemcpyDeviceToHost, e->stream));
+        if (prob != nullptr) {
+            // the reference trims / zero-pads the inverted audio to len(y) before predicting (:676-680); rows keep a zero tail
+            if (e->L > out_len)
+                B200X_CUDA_TRY(cudaMemset2DAsync(e->y.as<float>() + out_len, e->y_stride * sizeof(float), 0, (e->L - out_len) * sizeof(float), m, e->stream));
+            B200X_TRY(forward_chunk(e, m, e->L, nullptr, 0, e->prob.as<float>() + c0, e->logit.as<float>() + c0));
+        }
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));       // audio_host rows / y are reused by the next chunk
+    }
+    if (prob != nullptr) {
+        B200X_CUDA_TRY(cudaMemcpyAsync(prob, e->prob.p, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+        B200X_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
     return B200X_OK;
 }
 

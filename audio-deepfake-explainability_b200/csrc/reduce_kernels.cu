@@ -200,6 +200,25 @@ __global__ void delta_kernel(const float* __restrict__ prob, float baseline, int
     if (i < n) delta[i] = static_cast<double>(baseline) - static_cast<double>(prob[i]);
 }
 
+// Rational polyphase resampler (the track loader's resampling step): y[n] = up * sum_k h[n * down - k * up + c] x[k]
+// with c = (h_len - 1) / 2 (zero-phase FIR, odd length) - scipy.signal.resample_poly's definition with a user filter.  One
+// output sample per thread; the ~h_len / up taps of a phase are accumulated in float64 (the host path does the same).
+__global__ void resample_poly_kernel(const float* __restrict__ x, long long n_in, int up, int down, const double* __restrict__ h, int h_len,
+                                     float* __restrict__ y, long long n_out) {
+    const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (n >= n_out) return;
+    const long long c = (h_len - 1) / 2;
+    const long long pos = n * down + c;                    // tap index that multiplies x[0]
+    // taps j = pos - k * up must lie in [0, h_len): k from ceil((pos - h_len + 1) / up) to floor(pos / up)
+    long long k_hi = pos / up;
+    long long k_lo = pos - (h_len - 1);
+    k_lo = k_lo <= 0 ? 0 : (k_lo + up - 1) / up;
+    if (k_hi > n_in - 1) k_hi = n_in - 1;
+    double acc = 0.0;
+    for (long long k = k_lo; k <= k_hi; ++k) acc = fma(__ldg(h + (pos - k * up)), static_cast<double>(__ldg(x + k)), acc);
+    y[n] = static_cast<float>(acc * up);
+}
+
 __global__ void delta_dev_kernel(const float* __restrict__ prob, const float* __restrict__ baseline, int n, double* __restrict__ delta) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) delta[i] = static_cast<double>(__ldg(baseline)) - static_cast<double>(prob[i]);
@@ -243,6 +262,14 @@ extern "C" int b200x_head(const float* d_x, int copies, int tokens, int dim, con
 }
 
 extern "C" int b200x_head_slices(void) { return 8; }
+
+extern "C" int b200x_resample_poly(const float* d_x, int64_t n_in, int up, int down, const double* d_h, int h_len, float* d_y,
+                                   int64_t n_out, void* stream) {
+    B200X_REQUIRE(d_x && d_h && d_y && n_in > 0 && n_out > 0 && up > 0 && down > 0 && h_len > 0 && (h_len & 1), "resample_poly: bad argument");
+    resample_poly_kernel<<<static_cast<unsigned>((n_out + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_x, n_in, up, down, d_h, h_len, d_y, n_out);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
 
 extern "C" int b200x_delta_dev(const float* d_prob, const float* d_baseline, int n, double* d_delta, void* stream) {
     if (n <= 0) return B200X_OK;

@@ -13,7 +13,7 @@ from typing import Sequence, Any, Dict, List, NamedTuple, Optional, Tuple
 
 import numpy as np
 
-from . import dist, grid
+from . import dist, grid, mel_host
 from .audio_io import AudioDecodeError, load_audio, write_wav
 from .grid import FREQUENCY_BAND_PRESETS, smooth_band_keep_mask  # noqa: F401  (re-exported like the reference module)
 from .sonics_api import B200Predictor
@@ -45,7 +45,7 @@ class FrequencyBandPerturbation:
                  use_original_audio: bool = False, use_separation: bool = False, separation_model: str = "spleeter:2stems",
                  separation_targets: Tuple[str, ...] = ("vocals0", "accompaniment0"), normalize_loudness: bool = True,
                  lufs: Optional[float] = None, checkpoint_dir=None, save_perturbed_audio_only: bool = False,
-                 save_reversed_perturbed_audio_only: bool = False):
+                 save_reversed_perturbed_audio_only: bool = False, mel_seed: int = 0, nnls_iter: int = 16):
         if not isinstance(predictor, B200Predictor):
             raise TypeError(f"the B200 band sweep needs a B200Predictor, got {type(predictor).__name__}")
         self.predictor = predictor
@@ -58,8 +58,12 @@ class FrequencyBandPerturbation:
         self.sr, self.duration, self.n_mels = sr, duration, n_mels
         self.n_fft, self.hop_length, self.win_length, self.n_iter = n_fft, hop_length, win_length, n_iter
         self.spec_type = spec_type.lower()
-        if self.spec_type != "stft":
-            raise ValueError("FrequencyBandPerturbation currently supports only spec_type='stft'")
+        # The reference supports only 'stft' here (:357-359).  'mel' is a BUILDER-DEFINED extension: the band
+        # gain is evaluated at the centre frequency of every mel bin, applied to the power mel spectrogram and inverted with
+        # the seeded NNLS + Griffin-Lim of the mel occlusion variant (oracle/mel.py); no reference parity exists for it.
+        if self.spec_type not in ("stft", "mel"):
+            raise ValueError("FrequencyBandPerturbation supports spec_type='stft' (reference) or 'mel' (builder-defined)")
+        self.mel_seed, self.nnls_iter = int(mel_seed), int(nnls_iter)
         if (n_fft, hop_length, win_length) != (2048, 512, 2048):
             raise NotImplementedError("the CUDA STFT/iSTFT kernels are built for n_fft=2048, hop=512, win=2048")
         self.fmax = fmax if fmax is not None else sr // 2
@@ -97,6 +101,8 @@ class FrequencyBandPerturbation:
                                       **_ignored) -> Optional[FBDResult]:
         eng = self.predictor.engine
         sig = np.ascontiguousarray(np.asarray(sig, dtype=np.float32))
+        if self.spec_type == "mel":
+            return self._mel_component_importance(sig, component_name)
         gains = self.band_gains()
         _, world = dist.world()
         if world == 1 and len(self.bands) <= eng.copies_per_chunk:
@@ -118,6 +124,31 @@ class FrequencyBandPerturbation:
         rows = grid.band_bin_ranges(self.bands, self.sr, self.n_fft)
         importance_map = eng.band_map(rows, np.asarray(deltas, dtype=np.float64))
         return FBDResult(importance_map, amplitude_to_db_refmax(S), orig_prob, sig, S, batch)
+
+    def _mel_component_importance(self, sig: np.ndarray, component_name: str) -> FBDResult:
+        """FBP over the mel spectrogram (builder-defined): per band, mel bins are scaled by the band gain at their centre
+        frequency, the result is inverted (NNLS -> Griffin-Lim) and classified; ``importance_map`` is ``[n_mels, n_time]``."""
+        eng = self.predictor.engine
+        eng.set_track(sig)
+        basis = mel_host.mel_filterbank(self.sr, self.n_fft, self.n_mels, 0.0, None)
+        pinv, step = mel_host.nnls_operators(basis)
+        eng.set_mel_basis(basis, pinv, step)
+        S = eng.mel_spectrogram()
+        gains = mel_host.mel_band_gain_table(self.bands, self.sr, self.n_mels, self.attenuation, self.transition_mode,
+                                             self.transition_rel, self.transition_min_hz, self.transition_max_hz, self.transition_hz)
+        orig_prob = float(eng.predict_track())
+        rank, world = dist.world()
+        lo, hi = grid.shard_range(len(gains), rank, world)
+        local = (eng.mel_sweep(eng.MASK_BAND_GAIN, gains[lo:hi].astype(np.float32), self.n_iter, self.nnls_iter, self.mel_seed,
+                               first_index=lo) if hi > lo else np.zeros(0, np.float32))
+        probs = dist.gather_shards(local, len(gains))
+        deltas = [float(orig_prob - float(p)) for p in probs]
+        batch = [{"component": component_name, "low": float(lo_), "high": float(hi_), "importance": d}
+                 for (lo_, hi_), d in zip(self.bands, deltas)]
+        importance_map = np.zeros(S.shape, dtype=np.float64)
+        for rows, d in zip(mel_host.mel_band_rows(self.bands, self.sr, self.n_mels), deltas):
+            importance_map[rows, :] += d
+        return FBDResult(importance_map, mel_host.power_to_db_refmax(S), orig_prob, sig, S, batch)
 
     def compute_importance_batch(self, signals: Sequence[np.ndarray], component_name: str = "mixture") -> List[FBDResult]:
         """``_compute_component_importance`` for a batch of equal-length signals in shared launches (BASELINE configs[2]:
@@ -161,7 +192,7 @@ class FrequencyBandPerturbation:
 
     def _compute_importance(self, audio_path: str, track_output_dir: Optional[Path] = None, file_name: Optional[str] = None,
                             **_ignored) -> list:
-        y, _ = load_audio(audio_path, sr=self.sr, duration=self.duration, mono=True)
+        y, _ = load_audio(audio_path, sr=self.sr, duration=self.duration, mono=True, resample=self.predictor.engine.resample)
         audio_only = self.save_perturbed_audio_only or self.save_reversed_perturbed_audio_only
         res = self._compute_component_importance(y, "mixture", audio_path, audio_root=track_output_dir if audio_only else None,
                                                  file_name=file_name)

@@ -191,6 +191,78 @@ class Engine:
         _lib.check(self.lib.b200x_engine_band_audio(self._h, _ptr(g), g.shape[0], _ptr(out)), "band_audio")
         return out
 
+    # ------------------------------------------------------------------ track loader front
+    def resample(self, data: np.ndarray, native_sr: int, sr: int) -> np.ndarray:
+        """Polyphase resampling on the device (same filter and definition as ``audio_io.resample_poly_host``); the
+        ``resample=`` hook of ``audio_io.load_audio``."""
+        from math import gcd
+
+        from .audio_io import polyphase_filter
+        g = gcd(int(sr), int(native_sr))
+        up, down = int(sr) // g, int(native_sr) // g
+        x = np.ascontiguousarray(np.asarray(data, dtype=np.float32))
+        h = np.ascontiguousarray(polyphase_filter(up, down), dtype=np.float64)
+        n_out = -(-x.shape[0] * up // down)
+        y = np.empty(n_out, np.float32)
+        _lib.check(self.lib.b200x_engine_resample(self._h, _ptr(x), x.shape[0], up, down, _ptr(h), h.shape[0], _ptr(y), n_out), "resample")
+        return y
+
+    # ------------------------------------------------------------------ mel-domain variant (spec_type: mel)
+    def set_mel_basis(self, basis: np.ndarray, pinv: np.ndarray, step: float) -> None:
+        """Upload the mel filterbank ``[n_mels, 1025]``, its pseudo-inverse ``[1025, n_mels]`` and the NNLS step (mel_host.py)."""
+        b = np.ascontiguousarray(np.asarray(basis, dtype=np.float32))
+        p = np.ascontiguousarray(np.asarray(pinv, dtype=np.float32))
+        if b.ndim != 2 or b.shape[1] != 1025 or p.shape != (1025, b.shape[0]):
+            raise ValueError(f"basis [n_mels, 1025] / pinv [1025, n_mels] expected, got {b.shape} / {p.shape}")
+        _lib.check(self.lib.b200x_engine_set_mel_basis(self._h, b.shape[0], _ptr(b), _ptr(p), float(step)), "set_mel_basis")
+        self.n_mels = int(b.shape[0])
+
+    def mel_spectrogram(self) -> np.ndarray:
+        """Power mel spectrogram float32 ``[n_mels, n_time]`` of the current track (librosa.feature.melspectrogram)."""
+        _, t = self.track_shape()
+        out = np.empty((self.n_mels, t), np.float32)
+        _lib.check(self.lib.b200x_engine_mel_spectrogram(self._h, _ptr(out)), "mel_spectrogram")
+        return out
+
+    MASK_NONE, MASK_OCCLUDE, MASK_BAND_GAIN, MASK_KEEP_ONLY = 0, 1, 2, 3
+
+    def mel_sweep(self, mode: int, items: Optional[np.ndarray], n_iter: int, nnls_iter: int = 16, seed: int = 0, first_index: int = 0,
+                  occlusion_value: float = 0.0, momentum: float = 0.99, want_prob: bool = True, want_audio: bool = False):
+        """Mel-variant sweep: every perturbed mel spectrogram -> NNLS -> Griffin-Lim -> (probability, audio).  ``items``:
+        windows ``[n, 4]`` (t0, t1, mel0, mel1) for MASK_OCCLUDE / MASK_KEEP_ONLY, gains ``[n, n_mels]`` for MASK_BAND_GAIN,
+        ``None`` (one unperturbed copy) for MASK_NONE."""
+        wins = gains = None
+        if mode in (self.MASK_OCCLUDE, self.MASK_KEEP_ONLY):
+            wins = np.ascontiguousarray(np.asarray(items, dtype=np.int32)).reshape(-1, 4)
+            n = wins.shape[0]
+        elif mode == self.MASK_BAND_GAIN:
+            gains = np.ascontiguousarray(np.asarray(items, dtype=np.float32))
+            if gains.ndim != 2 or gains.shape[1] != self.n_mels:
+                raise ValueError(f"gains must be [n, {self.n_mels}], got {gains.shape}")
+            n = gains.shape[0]
+        else:
+            n = 1
+        _, t = self.track_shape()
+        prob = np.empty(n, np.float32) if want_prob else None
+        audio = np.empty((n, self.cfg.hop_length * (t - 1)), np.float32) if want_audio else None
+        _lib.check(self.lib.b200x_engine_mel_sweep(self._h, int(mode), _ptr(wins) if wins is not None else None,
+                                                   _ptr(gains) if gains is not None else None, n, float(occlusion_value), int(n_iter),
+                                                   int(nnls_iter), int(seed) & 0xFFFFFFFF, int(first_index), float(momentum),
+                                                   _ptr(prob) if prob is not None else None, _ptr(audio) if audio is not None else None),
+                   "mel_sweep")
+        if want_prob and want_audio:
+            return prob, audio
+        return prob if want_prob else audio
+
+    def saliency_map_shape(self, windows: np.ndarray, delta: np.ndarray, n_freq: int, n_time: int) -> np.ndarray:
+        """``saliency_map`` over an arbitrary ``[n_freq, n_time]`` grid (mel spectrogram rows)."""
+        w = np.ascontiguousarray(np.asarray(windows, dtype=np.int32)).reshape(-1, 4)
+        d = np.ascontiguousarray(np.asarray(delta, dtype=np.float64))
+        out = _pinned((n_freq, n_time), np.float64)
+        _lib.check(self.lib.b200x_engine_saliency_map_shape(self._h, _ptr(w), _ptr(d), w.shape[0], int(n_freq), int(n_time), _ptr(out)),
+                   "saliency_map_shape")
+        return out
+
     # ------------------------------------------------------------------ RISE (random keep masks generated on the device)
     def rise_sweep(self, n_masks: int, seed: int, keep_probability: float, first_mask: int = 0) -> np.ndarray:
         prob = np.empty(int(n_masks), np.float32)

@@ -70,7 +70,7 @@ class B200Predictor:
         return float(self.engine.predict(np.asarray(audio_wave, dtype=np.float32)))
 
     def predict_from_file(self, audio_path: Union[str, Path], sr: int = 44100, duration: Optional[float] = None) -> float:
-        y, _ = load_audio(str(audio_path), sr=sr, duration=duration, mono=True)
+        y, _ = load_audio(str(audio_path), sr=sr, duration=duration, mono=True, resample=self.engine.resample)
         return self.predict(y, sr)
 
     def predict_batch_from_files(self, audio_paths: Sequence[Union[str, Path]], sr: int = 44100,

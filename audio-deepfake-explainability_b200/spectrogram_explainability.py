@@ -15,7 +15,7 @@ from typing import Any, Dict, NamedTuple, Optional
 
 import numpy as np
 
-from . import dist, grid
+from . import dist, grid, mel_host
 from .audio_io import AudioDecodeError, load_audio, write_wav
 from .sonics_api import B200Predictor
 
@@ -97,7 +97,8 @@ class SpectrogramExplainability:
                  use_original_audio: bool = True, patch_time_frames: int = 2048, stride_time_frames: int = 2048,
                  patch_freq_percent: float = 25.0, stride_freq_percent: float = 25.0, n_masks: int = 500,
                  mask_probability: float = 0.5, checkpoint_dir=None, highlight_percent: float = 20.0,
-                 abs_threshold: float = 0.0, rise_seed: int = 0, tie_epsilon: float = 0.0):
+                 abs_threshold: float = 0.0, rise_seed: int = 0, tie_epsilon: float = 0.0, mel_seed: int = 0,
+                 nnls_iter: int = 16):
         if not isinstance(predictor, B200Predictor):
             raise TypeError("the B200 occlusion sweep needs a B200Predictor (the classifier runs inside the sweep); "
                             f"got {type(predictor).__name__}")
@@ -118,6 +119,11 @@ class SpectrogramExplainability:
         self.speculative_baseline = False   # True: always evaluate the baseline inside the sweep (see occlusion_map_from_wave)
         self.rise_seed = rise_seed          # the reference draws RISE masks from the unseeded numpy global RNG (:768)
         self.tie_epsilon = float(tie_epsilon)   # 0.0 = rank the raw importances like the reference; see grid.snap_ties
+        # spec_type='mel': the reference inverts with librosa's L-BFGS-B NNLS + Griffin-Lim from UNSEEDED random phases
+        # (:394-402), which no two runs reproduce; the build's inverse is seeded and its NNLS is the projected-gradient
+        # iteration of csrc/mel_domain.cu (oracle/mel.py restates both)
+        self.mel_seed, self.nnls_iter = int(mel_seed), int(nnls_iter)
+        self._mel_key = None
         self.highlight_percent, self.abs_threshold = highlight_percent, abs_threshold
         self.checkpoint = SpectrogramCheckpoint(checkpoint_dir) if checkpoint_dir else None
 
@@ -128,10 +134,9 @@ class SpectrogramExplainability:
         return cls(predictor=predictor, **spectrogram_explainer_kwargs(config, checkpoint_dir))
 
     # -- guards for the variants that have no reference parity ----------------
-    def _require_stft_occlusion(self, method: str = "occlusion") -> None:
-        if self.spec_type != "stft":
-            raise NotImplementedError("spec_type='mel' inverts through Griffin-Lim with unseeded random phase in the "
-                                      "reference (:394-402) and is not part of the parity path; use spec_type='stft'")
+    def _require_stft_occlusion(self, method: str = "occlusion", allow_mel: bool = False) -> None:
+        if self.spec_type != "stft" and not allow_mel:
+            raise NotImplementedError("spec_type='mel' is implemented for the occlusion method only")
         if self.method != method:
             raise NotImplementedError(f"this explainer was built with method={self.method!r}; "
                                       f"{'_compute_rise_map' if self.method == 'rise' else '_compute_occlusion_map'} is its entry point")
@@ -142,16 +147,39 @@ class SpectrogramExplainability:
         return float(self.predictor.predict(waveform, sr))          # errors propagate; no 0.0 fallback
 
     def _compute_spectrogram(self, y: np.ndarray):
-        """(S, S_db) with S = complex64 ``[1025, 1 + len(y)//512]`` computed on the GPU (librosa.stft semantics)."""
-        self._require_stft_occlusion(self.method)
-        self.predictor.engine.set_track(y)
-        S = self.predictor.engine.spectrogram()
+        """(S, S_db) on the GPU: complex64 STFT ``[1025, 1 + len(y)//512]`` (librosa.stft semantics) or, for
+        ``spec_type='mel'``, the float32 power mel spectrogram ``[n_mels, n_time]`` (librosa.feature.melspectrogram, :367-377)."""
+        self._require_stft_occlusion(self.method, allow_mel=True)
+        eng = self.predictor.engine
+        eng.set_track(y)
+        if self.spec_type == "mel":
+            self._ensure_mel_basis()
+            S = eng.mel_spectrogram()
+            return S, mel_host.power_to_db_refmax(S)
+        S = eng.spectrogram()
         return S, amplitude_to_db_refmax(S)
+
+    def _ensure_mel_basis(self) -> None:
+        """Upload the Slaney filterbank + NNLS operators once per configuration.  Like the reference, the forward filterbank
+        honours ``fmax`` (:375) while the inverse call passes none (:395-402): both are the same bank unless fmax < sr/2, in
+        which case - as in the reference - the inversion uses the [0, sr/2] bank."""
+        key = (self.sr, self.n_fft, self.n_mels, float(self.fmax))
+        if self._mel_key == key:
+            return
+        if float(self.fmax) != float(self.sr // 2) and float(self.fmax) != self.sr / 2:
+            raise NotImplementedError("spec_type='mel' with fmax != sr/2 pairs two different filterbanks in the reference "
+                                      "(forward :375 vs inverse :395-402); not supported")
+        basis = mel_host.mel_filterbank(self.sr, self.n_fft, self.n_mels, 0.0, None)
+        pinv, step = mel_host.nnls_operators(basis)
+        self.predictor.engine.set_mel_basis(basis, pinv, step)
+        self._mel_key = key
 
     # -- the hot path ---------------------------------------------------------------------------------
     def occlusion_map_from_wave(self, y: np.ndarray, occlusion_value: float = 0.0, baseline_threshold: float = 0.3,
                                 verbose: bool = True, want_spectrogram: bool = True) -> OcclusionResult:
-        self._require_stft_occlusion()
+        self._require_stft_occlusion(allow_mel=True)
+        if self.spec_type == "mel":
+            return self._mel_occlusion_map_from_wave(y, occlusion_value, baseline_threshold, verbose)
         eng = self.predictor.engine
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float32))
         eng.set_track(y)
@@ -190,6 +218,34 @@ class SpectrogramExplainability:
             print(f"    Completed | Mean importance: {importance_map.mean():.4f}, Max: {importance_map.max():.4f}")
         return OcclusionResult(importance_map, S_db, baseline_pred, y, S, patch_importances)
 
+    def _mel_occlusion_map_from_wave(self, y, occlusion_value, baseline_threshold, verbose) -> OcclusionResult:
+        """The occlusion loop over the MEL spectrogram (:663-703 with spec_type == 'mel'): window i zeroes mel bins
+        ``[f0, f1)`` of frames ``[t0, t1)``, the result is inverted (NNLS -> Griffin-Lim, ``n_iter`` iterations, phases of
+        index i) and classified.  One batched device sweep; the windows are sharded across ranks like the STFT ones."""
+        eng = self.predictor.engine
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float32))
+        S, S_db = self._compute_spectrogram(y)
+        n_freq, n_time = S.shape
+        windows = grid.occlusion_windows(n_freq, n_time, self.patch_time_frames, self.stride_time_frames,
+                                         self.patch_freq_percent, self.stride_freq_percent)
+        baseline_pred = float(eng.predict_track())
+        if verbose:
+            print(f"    Baseline prediction: {baseline_pred:.4f}")
+        if baseline_pred < baseline_threshold:
+            return OcclusionResult(None, S_db, baseline_pred, y, S, None)
+        rank, world = dist.world()
+        lo, hi = grid.shard_range(len(windows), rank, world)
+        local = (eng.mel_sweep(eng.MASK_OCCLUDE, windows[lo:hi], self.n_iter, self.nnls_iter, self.mel_seed, first_index=lo,
+                               occlusion_value=occlusion_value) if hi > lo else np.zeros(0, np.float32))
+        probs = dist.gather_shards(local, len(windows))
+        importances = [baseline_pred - float(p) for p in probs]
+        patch_importances = [
+            {"t_start": int(w[0]), "t_end": int(w[1]), "f_start": int(w[2]), "f_end": int(w[3]), "importance": imp}
+            for w, imp in zip(windows, importances)
+        ]
+        importance_map = eng.saliency_map_shape(windows, np.asarray(importances, dtype=np.float64), n_freq, n_time)
+        return OcclusionResult(importance_map, S_db, baseline_pred, y, S, patch_importances)
+
     # -- RISE (:722-806) -------------------------------------------------------------------------------
     def rise_map_from_wave(self, y: np.ndarray, baseline_threshold: float = 0.3, verbose: bool = True) -> RiseResult:
         """``n_masks`` i.i.d. Bernoulli(``mask_probability``) keep masks over the STFT, each -> iSTFT -> prediction;
@@ -219,12 +275,12 @@ class SpectrogramExplainability:
         return RiseResult(importance_map, S_db, baseline_pred, y, S)
 
     def _compute_rise_map(self, audio_path: str, baseline_threshold: float = 0.3, verbose: bool = True) -> RiseResult:
-        y, _ = load_audio(audio_path, sr=self.sr, duration=self.duration, mono=True)
+        y, _ = load_audio(audio_path, sr=self.sr, duration=self.duration, mono=True, resample=self.predictor.engine.resample)
         return self.rise_map_from_wave(y, baseline_threshold, verbose)
 
     def _compute_occlusion_map(self, audio_path: str, occlusion_value: float = 0.0, baseline_threshold: float = 0.3,
                                verbose: bool = True) -> OcclusionResult:
-        y, _ = load_audio(audio_path, sr=self.sr, duration=self.duration, mono=True)
+        y, _ = load_audio(audio_path, sr=self.sr, duration=self.duration, mono=True, resample=self.predictor.engine.resample)
         return self.occlusion_map_from_wave(y, occlusion_value, baseline_threshold, verbose)
 
     # -- top-k windows -> JSON / WAV ----------------------------------------------------------------------
@@ -266,7 +322,17 @@ class SpectrogramExplainability:
             return out
         if not self.use_original_audio:
             w = np.array([[m["t_start"], m["t_end"], m["f_start"], m["f_end"]] for m in windows_meta], np.int32)
-            full = self.predictor.engine.window_audio(w)
+            if self.spec_type == "mel":                  # masked_S = zeros except the patch -> mel_to_audio -> slice (:472-483)
+                eng = self.predictor.engine
+                audio = eng.mel_sweep(eng.MASK_KEEP_ONLY, w, self.n_iter, self.nnls_iter, self.mel_seed, first_index=1 << 20,
+                                      want_prob=False, want_audio=True)
+                full = []
+                for m, a in zip(windows_meta, audio):
+                    start = int(m["t_start"] * self.hop_length)
+                    n = max(1, (m["t_end"] - m["t_start"]) * self.hop_length)
+                    full.append(a[start: min(start + n, len(a))])
+            else:
+                full = self.predictor.engine.window_audio(w)
         for k, m in enumerate(windows_meta):
             n = max(1, (m["t_end"] - m["t_start"]) * self.hop_length)
             start = int(m["t_start"] * self.hop_length)

@@ -57,6 +57,11 @@ int b200x_device_count(int* count);
 int b200x_stft(const float* d_wave, int64_t n_samples, int n_fft, int hop, int reflect_pad, void* d_spec,
                int spec_stride, void* stream);
 
+/* librosa.stft (zero padding) of `copies` equal-length waves in one launch: wave c at d_waves + c * wave_stride floats,
+ * spectrum c at d_spec + c * spec_copy_stride complex values (Griffin-Lim: rebuilt = stft(istft(.)), librosa.griffinlim) */
+int b200x_stft_batch(const float* d_waves, int64_t n_samples, int64_t wave_stride, int copies, void* d_spec, int spec_stride,
+                     int64_t spec_copy_stride, void* stream);
+
 /* Batched librosa.istft of `copies` perturbed versions of one spectrogram; the perturbation is applied in the
  * load stage (mode = B200X_MASK_*), d_windows int32 [copies][4] = t0,t1,f0,f1, d_gains float [copies][1025].
  * Writes hop*(n_frames-1) samples per copy at d_y + copy*y_stride; d_sumsq (optional, pre-zeroed double[copies])
@@ -111,9 +116,37 @@ int b200x_mel_normalize_resize(const float* d_db, int db_frames, const float* d_
                                const int32_t* d_frame_range, void* d_partial, float* d_floor, void* d_img_t,
                                void* d_img_f, int ld_f, void* stream);
 
+/* Rational polyphase resampling by up / down with the odd-length zero-phase FIR d_h (float64, unit DC gain):
+ * y[n] = up * sum_k h[n * down - k * up + (h_len - 1) / 2] x[k], n < n_out = ceil(n_in * up / down)  (the resampling step of
+ * librosa.load(path, sr=...), src/spectrogram_explainability.py:601; librosa itself uses soxr_hq - see INTEGRATION.md) */
+int b200x_resample_poly(const float* d_x, int64_t n_in, int up, int down, const double* d_h, int h_len, float* d_y,
+                        int64_t n_out, void* stream);
+
 /* y[b] = sum_i masks[b][i] * stems[i]   (src/lime_explainer.py:283-301 composition) */
 int b200x_mix_stems(const float* d_stems, int64_t n_samples, int n_stems, const uint8_t* d_masks, int copies,
                     float* d_y, int64_t y_stride, void* stream);
+
+/* ---- mel-domain explainer variant (spec_type: mel; src/spectrogram_explainability.py:367-377, 394-402).  The reference's
+ * inverse (librosa mel_to_audio: L-BFGS-B NNLS + Griffin-Lim from UNSEEDED random phases) is not reproducible, so these
+ * kernels implement the builder-defined arithmetic restated in oracle/mel.py.  Spectra are frame-major, 1028 elements a row.
+ * d_basis: dense float [n_mels][1025] filterbank; d_bin_range int32 [n_mels][2] non-zero bins of each filter; d_bin_first
+ * int32 [1025] / d_bin_w float [1025][2]: the (at most two, adjacent) filters each bin feeds; d_pinv_t float [n_mels][1025]. */
+/* d_mel[t][i] = sum_k basis[i][k] |S[t][k]|^2   (librosa.feature.melspectrogram, power 2) */
+int b200x_mel_power(const void* d_spec, int spec_stride, int n_frames, int n_mels, const float* d_basis, const int32_t* d_bin_range,
+                    float* d_mel, void* stream);
+/* per copy and frame t in d_frame_range[copy] = [fa, fb): B = mel[t] with the perturbation applied (mode B200X_MASK_NONE /
+ * OCCLUDE / KEEP_ONLY with d_windows (t0,t1,mel0,mel1) / BAND_GAIN with d_gains [copies][n_mels]); X = max(0, pinv B), then
+ * nnls_iter steps X <- max(0, X - step basis^T (basis X - B)); d_mag[copy][t][k] = sqrt(X[k])  (mel_to_stft, power 2) */
+int b200x_mel_nnls(const float* d_mel, int n_frames, int n_mels, int copies, int mode, const int32_t* d_windows,
+                   float occlusion_value, const float* d_gains, const float* d_basis, const int32_t* d_bin_range,
+                   const int32_t* d_bin_first, const float* d_bin_w, const float* d_pinv_t, float step, int nnls_iter,
+                   const int32_t* d_frame_range, int max_range_frames, float* d_mag, int64_t mag_copy_stride, void* stream);
+/* Griffin-Lim: C = mag * exp(2 pi i u) with u = hash(seed, first_index + copy, cell) / 2^32 (the RISE hash), and the update
+ * a = rebuilt - coef * tprev; C = mag * a / (|a| + tiny)   (librosa.griffinlim, momentum: coef = m / (1 + m); 0 first) */
+int b200x_gl_init(const float* d_mag, int64_t mag_copy_stride, void* d_c, int64_t c_copy_stride, int copies, int n_frames,
+                  uint32_t seed, int first_index, void* stream);
+int b200x_gl_update(const void* d_rebuilt, const void* d_tprev, const float* d_mag, int64_t mag_copy_stride, void* d_c,
+                    int64_t c_copy_stride, int copies, int n_frames, float coef, void* stream);
 
 /* tcgen05 GEMM  C[M,N] = A[M,K] . W[N,K]^T, bf16 operands (row-major, K contiguous), fp32 accumulation in TMEM,
  * fused epilogue per B200X_GEMM_OUT_*.  block_n in {128,192,208,256}.  B200X_GEMM_OUT_F32_RESID accumulates in place
@@ -238,6 +271,10 @@ int b200x_engine_occluded_audio(b200x_engine* e, const int32_t* windows, int n, 
 /* Perturbed audio of the FBP bands (for separated_bands WAVs, src/dsp_band_ops.py:608-639): float [n][hop*(n_time-1)]. */
 int b200x_engine_band_audio(b200x_engine* e, const float* gains, int n, float* audio_host);
 
+/* Track-loader front: b200x_resample_poly on host buffers (upload, one launch, read back) */
+int b200x_engine_resample(b200x_engine* e, const float* x_host, int64_t n_in, int up, int down, const double* h_host, int h_len,
+                          float* y_host, int64_t n_out);
+
 /* Reductions on host buffers (map is float64 [n_freq][n_time]). */
 int b200x_engine_saliency_map(b200x_engine* e, const int32_t* windows, const double* delta, int n, double* map_host);
 /* RISE (src/spectrogram_explainability.py:722-806): probabilities of masks first_mask .. first_mask + n - 1 of the track set
@@ -247,6 +284,22 @@ int b200x_engine_rise_sweep(b200x_engine* e, int first_mask, int n, uint32_t see
 int b200x_engine_rise_audio(b200x_engine* e, int first_mask, int n, uint32_t seed, double keep_probability, float* audio_host);
 int b200x_engine_rise_map(b200x_engine* e, const double* pred, int n, uint32_t seed, double keep_probability, double* map_host);
 int b200x_engine_band_map(b200x_engine* e, const int32_t* band_rows, const double* delta, int n, double* map_host);
+/* saliency_map over an arbitrary [n_freq][n_time] grid (the mel variant's map has n_mels rows) */
+int b200x_engine_saliency_map_shape(b200x_engine* e, const int32_t* windows, const double* delta, int n, int n_freq, int n_time,
+                                    double* map_host);
+
+/* Mel-domain variant.  set_mel_basis: dense filterbank float [n_mels][1025] (librosa.filters.mel, Slaney), its pseudo-inverse
+ * float [1025][n_mels] and 1 / ||basis||_2^2 (host float64 linear algebra, mel_host.py).  mel_spectrogram: power mel of the
+ * current track, float [n_mels][n_time] (librosa layout).  mel_sweep: for every perturbed copy i
+ *     y_i = griffinlim(sqrt(nnls(basis, perturbed mel)), n_iter, phases of index first_index + i), prob[i] = predict(y_i)
+ * (src/spectrogram_explainability.py:663-703 with spec_type == 'mel'); windows int32 [n][4] = t0,t1,mel0,mel1 for
+ * B200X_MASK_OCCLUDE / KEEP_ONLY, gains float [n][n_mels] for BAND_GAIN (the builder's FBP-mel); prob and audio_host
+ * (float [n][hop * (n_time - 1)]) are host buffers, either may be NULL. */
+int b200x_engine_set_mel_basis(b200x_engine* e, int n_mels, const float* basis, const float* pinv, float step);
+int b200x_engine_mel_spectrogram(b200x_engine* e, float* mel_host);
+int b200x_engine_mel_sweep(b200x_engine* e, int mode, const int32_t* windows, const float* gains, int n, float occlusion_value,
+                           int n_iter, int nnls_iter, uint32_t seed, int first_index, float momentum, float* prob,
+                           float* audio_host);
 int b200x_engine_rank(b200x_engine* e, const double* values, int n, int mode, int32_t* order_host);
 
 /* Introspection for tests / profiling: device pointer of a named intermediate of the LAST processed chunk

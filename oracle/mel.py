@@ -64,7 +64,7 @@ def slaney_mel_filterbank(sr: float, n_fft: int, n_mels: int, fmin: float = 0.0,
         upper = ramps[i + 2] / fdiff[i + 1]
         weights[i] = np.maximum(0, np.minimum(lower, upper))
     enorm = 2.0 / (mel_f[2: n_mels + 2] - mel_f[:n_mels])
-    weights *= enorm[:, np.newaxis].astype(np.float32)
+    weights *= enorm[:, np.newaxis]                    # in place: float32(float64 product), like librosa
     return weights
 
 
