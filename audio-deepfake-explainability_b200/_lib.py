@@ -10,7 +10,8 @@ import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libb200xai.so"
+# B200X_LIB_PATH: developer override for A/B runs of kernel-variant builds (build.py B200X_LIB_OUT); default = the in-tree library
+LIB_PATH = Path(os.environ["B200X_LIB_PATH"]) if os.environ.get("B200X_LIB_PATH") else HERE / "libb200xai.so"
 
 c_i32p = C.POINTER(C.c_int32)
 c_f32p = C.POINTER(C.c_float)

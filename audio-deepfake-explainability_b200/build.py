@@ -13,7 +13,9 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-LIB = HERE / "libb200xai.so"
+# developer overrides for A/B builds of kernel variants: B200X_LIB_OUT=<path of the .so>  B200X_NVCC_EXTRA="-DNAME=value ..."
+LIB = Path(os.environ["B200X_LIB_OUT"]) if os.environ.get("B200X_LIB_OUT") else HERE / "libb200xai.so"
+EXTRA = os.environ.get("B200X_NVCC_EXTRA", "").split()
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
@@ -43,12 +45,12 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
     nvcc = _nvcc()
-    obj_dir = HERE / "build"
+    obj_dir = HERE / ("build" if not EXTRA else "build_" + "_".join(t.strip("-D").replace("=", "") for t in EXTRA))
     obj_dir.mkdir(exist_ok=True)
 
     def compile_one(src: Path):
         obj = obj_dir / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (obj_dir / (src.stem + ".ptxas.log")).write_text(r.stderr)
         if r.returncode != 0:

@@ -150,8 +150,14 @@ struct IstftParams {
 
 // MODE is a template parameter: the mask is evaluated per bin inside the fully unrolled load stage, and a run-time mode
 // cost an ISETP / BRA pair per element there (ncu: a quarter of the kernel's samples sat in that stage)
+#ifndef B200X_ISTFT_MIN_CTAS
+#define B200X_ISTFT_MIN_CTAS 1
+#endif
+#ifndef B200X_MEL_MIN_CTAS
+#define B200X_MEL_MIN_CTAS 3
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(DSP_THREADS)
+__global__ void __launch_bounds__(DSP_THREADS, B200X_ISTFT_MIN_CTAS)
 istft_masked_kernel(IstftParams p) {
     extern __shared__ __align__(16) float2 dsp_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,7 +329,7 @@ struct MelParams {
     const int* frame_range;    // optional [copies][2] = [ma, mb): only these frames are computed
 };
 
-__global__ void __launch_bounds__(DSP_THREADS, 3)      // 168 registers, 74 KB of shared memory: three CTAs per SM
+__global__ void __launch_bounds__(DSP_THREADS, B200X_MEL_MIN_CTAS)      // 3: 168 registers, 74 KB of shared memory: three CTAs per SM
 mel_db_kernel(MelParams p) {
     extern __shared__ __align__(16) float2 dsp_smem[];
     __shared__ float s_max[DSP_WARPS];
