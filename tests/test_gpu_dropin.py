@@ -111,14 +111,22 @@ def test_occlusion_process_audio_file_writes_reference_layout(predictor, track, 
 def test_unsupported_variants_fail_loudly(predictor):
     with pytest.raises(TypeError):
         SpectrogramExplainability(object(), sr=SR)
-    ex = SpectrogramExplainability(predictor, sr=SR, spec_type="mel", method="occlusion")
+    ex = SpectrogramExplainability(predictor, sr=SR, spec_type="mel", method="rise")       # mel is built for occlusion only
     with pytest.raises(NotImplementedError):
+        ex.rise_map_from_wave(np.zeros(SR, np.float32))
+    ex = SpectrogramExplainability(predictor, sr=SR, spec_type="mel", method="occlusion", fmax=4000)
+    with pytest.raises(NotImplementedError):                                                # forward / inverse filterbanks would differ (:375 vs :395)
         ex.occlusion_map_from_wave(np.zeros(SR, np.float32))
     ex = SpectrogramExplainability(predictor, sr=SR, spec_type="stft", method="rise")
     with pytest.raises(NotImplementedError):
         ex.occlusion_map_from_wave(np.zeros(SR, np.float32))
+    ex = SpectrogramExplainability(predictor, sr=SR, spec_type="stft", method="occlusion", n_fft=1024)
+    with pytest.raises(NotImplementedError):                                                # kernels are built for 2048 / 512 / 2048
+        ex.occlusion_map_from_wave(np.zeros(SR, np.float32))
     with pytest.raises(ValueError):
-        FrequencyBandPerturbation(predictor, spec_type="mel", sr=SR)
+        SpectrogramExplainability(predictor, sr=SR, spec_type="cqt")
+    with pytest.raises(ValueError):
+        FrequencyBandPerturbation(predictor, spec_type="cqt", sr=SR)
 
 
 @pytest.mark.parametrize("normalize", [False, True])
