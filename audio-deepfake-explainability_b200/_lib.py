@@ -50,6 +50,8 @@ SIGNATURES = {
     "b200x_mix_stems": (C.c_int, [VP, C.c_int64, C.c_int, VP, C.c_int, VP, C.c_int64, VP]),
     "b200x_gemm_bf16": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_int, C.c_int,
                                   VP, C.c_int, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP]),
+    "b200x_gemm_resid_ln_bf16": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_int, VP, VP, VP, C.c_float, VP, C.c_int,
+                                           C.c_int, VP]),
     "b200x_attention": (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP]),
     "b200x_layernorm": (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP, VP, C.c_int, C.c_int, C.c_float, VP, VP, C.c_int, VP]),
     "b200x_head_slices": (C.c_int, []),
@@ -106,6 +108,7 @@ SIGNATURES = {
     "b200x_engine_launch_count": (C.c_int64, [VP]),
     "b200x_engine_set_timing": (C.c_int, [VP, C.c_int]),
     "b200x_engine_set_graphs": (C.c_int, [VP, C.c_int]),
+    "b200x_engine_set_fused_layernorm": (C.c_int, [VP, C.c_int]),
     "b200x_engine_get_timing": (C.c_int, [VP, VP, VP]),
     "b200x_engine_stream": (VP, [VP]),
     "b200x_engine_synchronize": (C.c_int, [VP]),

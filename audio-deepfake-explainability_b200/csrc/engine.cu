@@ -115,6 +115,7 @@ struct b200x_engine {
     uint64_t graph_clock = 0;
     static constexpr size_t max_graphs = 16;   // least-recently-used shapes beyond this are destroyed (tracks of many lengths)
     bool use_graphs = true;
+    bool fuse_ln = true;       // LayerNorm as a tail of the residual GEMM before it (gemm_resid_ln) instead of a pass of its own
     DevBuf prob_chunk, logit_chunk, ranges_chunk;      // fixed addresses baked into the graphs
 
     // optional per-kernel-class CUDA-event timing (bench roofline breakdown)
@@ -213,10 +214,18 @@ int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const dou
     // 229-copy activations are 0.25-1.1 GB per tensor).  The direction is a launch ARGUMENT (no process-wide state).
     int rev = 1;                          // the first LayerNorm walks forward (rev flips to 0 before its launch)
     auto dir = [&]() { if (e->alternate) rev ^= 1; else rev = 0; return rev; };
+    // With the LayerNorm tail (default) fc2 leaves h = LayerNorm_1(x) of the NEXT block behind (b200x_gemm_resid_ln_bf16), so
+    // LN1 is a pass of its own only in the first block.  LN2 stays a separate pass: behind the K = 384 attention projection
+    // the tail measured slower than the two kernels (its re-read of x misses L2; see gemm_tcgen05.cu).
+    const bool fuse = e->fuse_ln && D % 128 == 0 && D <= 384;
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
-        TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n1_g.as<float>(), w.n1_b.as<float>(), nullptr, nullptr, 0, 0,
-                                  c.block_ln_eps, e->h.p, nullptr, dir(), s));
+        const bool last = l + 1 == c.num_layers;
+        if (!fuse || l == 0) {
+            TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n1_g.as<float>(), w.n1_b.as<float>(), nullptr, nullptr, 0, 0,
+                                      c.block_ln_eps, e->h.p, nullptr, dir(), s));
+            e->launches += 1;
+        }
         TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D, D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
                                   c.qkv_bias ? w.qkv_b.as<float>() : nullptr, 0, nullptr, nullptr, 0, 0, 0, dir(), s));
         TIMED(KC_ATTN, b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, dir(), s));
@@ -224,11 +233,18 @@ int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const dou
                                   w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, dir(), s));
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
                                   c.block_ln_eps, e->h.p, nullptr, dir(), s));
+        e->launches += 1;
         TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp, D), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
                                   w.fc1_b.as<float>(), 1, nullptr, nullptr, 0, 0, 0, dir(), s));
-        TIMED(KC_GEMM, b200x_gemm_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, pick_block_n(D), e->x.p, D,
-                                  B200X_GEMM_OUT_F32_RESID, w.fc2_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, dir(), s));
-        e->launches += 7;
+        if (fuse && !last) {
+            LayerW& wn = e->layers[l + 1];
+            TIMED(KC_GEMM, b200x_gemm_resid_ln_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, e->x.as<float>(), D, w.fc2_b.as<float>(),
+                                               wn.n1_g.as<float>(), wn.n1_b.as<float>(), c.block_ln_eps, e->h.p, D, dir(), s));
+        } else {
+            TIMED(KC_GEMM, b200x_gemm_bf16(e->hid.p, e->Hp, w.fc2_w.p, e->Hp, M, D, e->Hp, pick_block_n(D), e->x.p, D,
+                                      B200X_GEMM_OUT_F32_RESID, w.fc2_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, dir(), s));
+        }
+        e->launches += 5;
         if (e->trace)
             B200X_CUDA_TRY(cudaMemcpyAsync(e->trace + static_cast<size_t>(l + 1) * M * D, e->x.p, xbytes, cudaMemcpyDeviceToDevice, s));
     }
@@ -1300,6 +1316,17 @@ extern "C" int b200x_engine_set_alternate(b200x_engine* e, int enable) {
         for (auto& kv : e->graphs) {                  // the direction is baked into captured launches: drop the graphs
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         }
+        e->graphs.clear();
+    }
+    return B200X_OK;
+}
+
+extern "C" int b200x_engine_set_fused_layernorm(b200x_engine* e, int enable) {
+    B200X_REQUIRE(e != nullptr, "set_fused_layernorm: engine is NULL");
+    if (e->fuse_ln != (enable != 0)) {
+        e->fuse_ln = enable != 0;
+        for (auto& kv : e->graphs)                        // the launch sequence is baked into the captured graphs
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         e->graphs.clear();
     }
     return B200X_OK;

@@ -18,6 +18,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "layernorm_rows.cuh"
 
 namespace b200x {
 
@@ -105,7 +106,7 @@ __device__ __forceinline__ void convert_columns(const uint32_t* r, uint32_t* w, 
 
 // bf16 / residual epilogue of one 128 x BN accumulator tile for one epilogue warp (lane quarter of TMEM, every other
 // column group): TMEM -> registers -> bias (+GELU) -> swizzled slab -> one TMA tensor store (or reduce-add) per slab.
-template <int BN>
+template <int BN, int NBUF = 2>
 __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
                                                     uint8_t* slab, int& buf, uint32_t t_row, int m_warp, int n_blk, int half, int lane,
                                                     long long* pc = nullptr) {
@@ -123,11 +124,13 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const C
             // bulk_wait_read<1> no longer proves that the store which last used it has been read
             if (m_warp >= p.M || n0 >= p.N) continue;
             if (pc) pt = clock64();
-            bulk_wait_read<1>();                         // the store that last used this buffer has read it
-            __syncwarp();
+            if (NBUF == 2) {
+                bulk_wait_read<1>();                     // the store that last used this buffer has read it
+                __syncwarp();
+            }
             if (pc) { const long long t = clock64(); pc[0] += t - pt; pt = t; }
             uint8_t* dst = slab + buf * GEMM_SLAB_BYTES;
-            buf ^= 1;
+            if (NBUF == 2) buf ^= 1;
             if (full) {
                 uint32_t r[64];
                 tmem_ld32(t_row + c, r);
@@ -137,6 +140,10 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const C
                 uint32_t w[32];
                 if (p.act_gelu) convert_columns<64, true>(r, w, p.bias, n0, p.N);
                 else convert_columns<64, false>(r, w, p.bias, n0, p.N);
+                if (NBUF == 1) {                         // single slab: the previous store had the conversion time to read it
+                    bulk_wait_read<0>();
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(dst + lane * 128 + ((j ^ sw) << 4)) =
@@ -148,6 +155,10 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const C
                 uint32_t w[8];
                 if (p.act_gelu) convert_columns<16, true>(r, w, p.bias, n0, p.N);
                 else convert_columns<16, false>(r, w, p.bias, n0, p.N);
+                if (NBUF == 1) {
+                    bulk_wait_read<0>();
+                    __syncwarp();
+                }
                 *reinterpret_cast<uint4*>(dst + lane * 32) = make_uint4(w[0], w[1], w[2], w[3]);       // dense 32-byte rows
                 *reinterpret_cast<uint4*>(dst + lane * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
             }
@@ -519,6 +530,261 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------ residual GEMM + LayerNorm tail
+// x += A . W^T + bias (fp32 residual stream, TMA reduce-add as above), then h = LayerNorm(x) in bf16 for the projection that
+// follows (attention proj -> LN2 -> fc1; fc2 -> next block's LN1 -> QKV).  The separate LayerNorm pass read the 484 MB
+// residual stream back from HBM a few microseconds after the residual GEMM had updated it; here a CTA normalises its own 128
+// rows as soon as its reduce-adds for ALL column tiles of the row tile have completed, while they still sit in L2:
+//   warps 16 / 17: TMA producer / MMA issuer as in gemm2_bf16_tn_kernel, but row-tile major: the pair finishes every column
+//                  tile of a 256-row tile before it moves on
+//   warps 8-15   : epilogue (reduce-add); after the last column tile each warp waits for its bulk groups to COMPLETE
+//                  (cp.async.bulk.wait_group 0: the adds are performed in L2) and arrives on x_ready[row tile & 1]
+//   warps 0-7    : LayerNorm tail, 16 rows per warp, one warp per row, the arithmetic of layernorm_kernel bit for bit (same
+//                  summation tree), four rows in flight per warp; ld.global.cg (L2) -> bf16 h rows.  They lag one row tile
+//                  behind the MMAs; ln_done[] stops the epilogue from lapping them.
+// Measured (229 copies, profiles/r02_h_gemm_resid_ln.txt): fc2 + tail 379 us against 310 + 107 us for the two kernels, but
+// proj + tail 322 us against 211 + 107 us: ncu shows the tail's re-read of x coming from DRAM after all (1.17 GB read per call
+// = A + reduce-add RMW + 0.45 GB) - lines produced by TMA reduce-adds are not retained in L2 (an evict_last cache hint on the
+// reduction changes nothing), so the K = 384 projection, already at 5.7 TB/s, only gets longer.  The engine therefore uses
+// the tail behind fc2 (K = 1040, tensor-bound with HBM headroom) and keeps the separate LayerNorm pass behind proj.
+constexpr int GEMM_RLN_LN_WARPS = 8;
+// warp roles: the SM's warp arbiter prefers HIGHER warp ids, and a TMA producer / MMA issuer that loses its issue slots to the
+// eight busy LayerNorm warps delays every tcgen05.mma - so the single-thread roles sit on top, the LayerNorm tail at the bottom
+constexpr int GEMM_RLN_W_EPI = GEMM_RLN_LN_WARPS;                  // 8..15 (quarter = warp & 3 still names the TMEM lane quarter)
+constexpr int GEMM_RLN_W_TMA = GEMM_RLN_W_EPI + GEMM_EPI_WARPS;   // 16
+constexpr int GEMM_RLN_W_MMA = GEMM_RLN_W_TMA + 1;                // 17
+constexpr int GEMM_RLN_THREADS = 32 * (GEMM_RLN_W_MMA + 1);
+constexpr int GEMM_RLN_ROWS_PER_BATCH = 4;
+
+struct GemmLnTail {
+    const float* x;          // [M][ldx] fp32 residual stream (the GEMM's reduce-add target)
+    int ldx;
+    const float* gamma;      // [N]
+    const float* beta;       // [N]
+    float eps;
+    __nv_bfloat16* h;        // [M][ldh] bf16 LayerNorm(x)
+    int ldh;
+};
+
+// fp32 residual epilogue of one accumulator tile for one epilogue warp: x += acc + bias via TMA reduce-add
+template <int BN>
+__device__ __forceinline__ void epilogue_resid_tile(const GemmParams& p, const CUtensorMap& tmC, uint8_t* slab, int& buf, uint32_t t_row,
+                                                    int m_warp, int n_blk, int half, int lane) {
+    const int sw = lane & 7;
+    constexpr int NG = BN / 32;
+#pragma unroll 1
+    for (int g = half; g < NG; g += 2) {
+        const int c = g * 32;
+        const int n0 = n_blk * BN + c;
+        if (m_warp >= p.M || n0 >= p.N) continue;
+        bulk_wait_read<1>();
+        __syncwarp();
+        uint8_t* dst = slab + buf * GEMM_SLAB_BYTES;
+        buf ^= 1;
+        uint32_t r[32];
+        tmem_ld32(t_row + c, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && n0 + 4 * j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * j));
+            const float4 v = make_float4(__uint_as_float(r[4 * j]) + b.x, __uint_as_float(r[4 * j + 1]) + b.y,
+                                         __uint_as_float(r[4 * j + 2]) + b.z, __uint_as_float(r[4 * j + 3]) + b.w);
+            *reinterpret_cast<float4*>(dst + lane * 128 + ((j ^ sw) << 4)) = v;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+            tma_reduce_add_2d(&tmC, dst, n0, m_warp);
+            bulk_commit();
+        }
+    }
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_RLN_THREADS, 1)
+gemm2_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, GemmParams p, GemmLnTail q) {
+    using L = Gemm2Smem<BN>;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    constexpr int STAGES = L::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* x_ready = tempty_bar + 2;                  // [2] this CTA's rows of the row tile are final in L2
+    uint64_t* ln_done = x_ready + 2;                     // [2] the LayerNorm warps have consumed x_ready[b]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_done + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == GEMM_RLN_W_TMA && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
+            mbar_init(&x_ready[s], GEMM_EPI_WARPS);
+            mbar_init(&ln_done[s], GEMM_RLN_LN_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == GEMM_RLN_W_MMA) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == GEMM_RLN_W_TMA) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mt = pair; mt < m_tiles; mt += n_pairs) {
+                const int m_blk = p.reverse ? m_tiles - 1 - mt : mt;
+                for (int n_blk = 0; n_blk < n_tiles; ++n_blk) {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                        const uint32_t leader_full = mapa_shared(&full_bar[stage], 0);
+                        tma_load_2d_pair(sa, &tmA, leader_full, kb * GEMM_BK, m_blk * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM);
+                        tma_load_2d_pair(sa + L::A_BYTES, &tmB, leader_full, kb * GEMM_BK, n_blk * BN + static_cast<int>(rank) * (BN / 2));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == GEMM_RLN_W_MMA) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, false);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int mt = pair; mt < m_tiles; mt += n_pairs) {
+                for (int n_blk = 0; n_blk < n_tiles; ++n_blk) {
+                    mbar_wait(&tempty_bar[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * BN;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+                        const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                            umma_ss_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_pair(&tfull_bar[as]);
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= GEMM_RLN_W_EPI) {
+        // ------------------------------------------------------------------ epilogue (warps 8..15 of both CTAs)
+        const int quarter = warp & 3;
+        const int half = (warp - GEMM_RLN_W_EPI) >> 2;
+        uint8_t* slab = smem + L::EPI_OFFSET + (warp - GEMM_RLN_W_EPI) * GEMM_EPI_WARP_BYTES;
+        int as = 0, buf = 0, tile_parity = 0, it = 0;
+        uint32_t aphase = 0;
+        const uint32_t leader_tempty0 = mapa_shared(&tempty_bar[0], 0), leader_tempty1 = mapa_shared(&tempty_bar[1], 0);
+        for (int mt = pair; mt < m_tiles; mt += n_pairs, ++it) {
+            const int m_blk = p.reverse ? m_tiles - 1 - mt : mt;
+            for (int n_blk = 0; n_blk < n_tiles; ++n_blk, ++tile_parity) {
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const int m_warp = m_blk * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32;
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+                epilogue_resid_tile<BN>(p, tmC, slab, buf, t_row, m_warp, n_blk, half ^ (tile_parity & 1), lane);
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) mbar_arrive_cluster(as == 0 ? leader_tempty0 : leader_tempty1);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            // every reduce-add of this warp into the row tile has been PERFORMED (not merely read out of the slab)
+            bulk_wait<0>();
+            const int b = it & 1, u = it >> 1;
+            if (u > 0) mbar_wait(&ln_done[b], (u - 1) & 1);   // the LayerNorm warps have seen the previous use of x_ready[b]
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&x_ready[b]);
+        }
+    } else {
+        // ------------------------------------------------------------------ LayerNorm tail (warps 0..7 of both CTAs)
+        constexpr int ROWS_PER_WARP = GEMM_BM / GEMM_RLN_LN_WARPS;           // 16
+        constexpr int RB = GEMM_RLN_ROWS_PER_BATCH;
+        const int pw = warp;
+        const int D = p.N;
+        const int vpl = D / 128;                                             // float4 vectors per lane (<= 3)
+        const float inv_d = 1.0f / static_cast<float>(D);
+        int it = 0;
+        for (int mt = pair; mt < m_tiles; mt += n_pairs, ++it) {
+            const int m_blk = p.reverse ? m_tiles - 1 - mt : mt;
+            const int b = it & 1, u = it >> 1;
+            mbar_wait(&x_ready[b], u & 1);
+            fence_proxy_async_all();                                         // async-proxy (TMA reduce) writes -> generic-proxy reads
+            const long long row0 = static_cast<long long>(m_blk) * 2 * GEMM_BM + static_cast<long long>(rank) * GEMM_BM + pw * ROWS_PER_WARP;
+#pragma unroll 1
+            for (int r0 = 0; r0 < ROWS_PER_WARP; r0 += RB) {
+                if (row0 + r0 >= p.M) break;
+                // RB rows in flight per warp; every step runs over all RB rows before the next one starts, so the shuffle /
+                // divide / rsqrt latencies of the rows overlap (written row after row, ptxas serialises the chains)
+                float4 v[RB][3];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const long long row = row0 + r0 + r;
+                    const float4* src = reinterpret_cast<const float4*>(q.x + row * q.ldx);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        v[r][i] = (row < p.M && i < vpl) ? __ldcg(src + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                layernorm_rows<RB>(v, vpl, inv_d, q.eps, q.gamma, q.beta, lane, [&](int r, int i, float4 o) {
+                    const long long row = row0 + r0 + r;
+                    if (row < p.M)
+                        reinterpret_cast<uint2*>(q.h + row * q.ldh)[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                });
+            }
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&ln_done[b]);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == GEMM_RLN_W_MMA) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+static int launch_gemm2_resid_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                                 const GemmLnTail& q, cudaStream_t stream) {
+    using L = Gemm2Smem<BN>;
+    int num_sms = 0;
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(gemm2_resid_ln_kernel<BN>), L::TOTAL));
+    B200X_TRY(device_sm_count(&num_sms));
+    const int pairs = std::min(ceil_div(p.M, 2 * GEMM_BM), num_sms / 2);
+    gemm2_resid_ln_kernel<BN><<<2 * pairs, GEMM_RLN_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, p, q);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
                        const GemmParams& p, cudaStream_t stream) {
@@ -609,4 +875,34 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
         case 256: return launch_gemm<256>(tmA, tmB, tmC, tmCtail, p, s);
         default: return set_error(B200X_ERR_INVALID, "gemm: unsupported block_n %d (128/192/208/256)", block_n);
     }
+}
+
+extern "C" int b200x_gemm_resid_ln_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, float* d_x, int ldx,
+                                        const float* d_bias, const float* d_gamma, const float* d_beta, float eps, void* d_h, int ldh,
+                                        int reverse, void* stream) {
+    B200X_REQUIRE(d_a && d_w && d_x && d_gamma && d_beta && d_h, "gemm_resid_ln: NULL argument");
+    B200X_REQUIRE(M > 0 && K > 0, "gemm_resid_ln: empty problem");
+    B200X_REQUIRE(N % 128 == 0 && N <= 384, "gemm_resid_ln: N=%d (the LayerNorm width) must be a multiple of 128 up to 384", N);
+    B200X_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_resid_ln: K / lda / ldw must be multiples of 8");
+    B200X_REQUIRE(ldx % 4 == 0 && ldx >= N && ldh % 4 == 0 && ldh >= N, "gemm_resid_ln: ldx / ldh must be multiples of 4 and >= N");
+    B200X_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_h) & 7) == 0 &&
+                  (reinterpret_cast<uintptr_t>(d_gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_beta) & 15) == 0 &&
+                  (d_bias == nullptr || (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0), "gemm_resid_ln: misaligned pointer");
+    constexpr int BN = 192;
+    CUtensorMap tmA, tmB, tmC;
+    const uint64_t da[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t sa[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t ba[2] = {GEMM_BK, GEMM_BM};
+    B200X_TRY(make_tmap_bf16(&tmA, d_a, 2, da, sa, ba));
+    const uint64_t dw[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t sw[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t bw[2] = {GEMM_BK, BN / 2};
+    B200X_TRY(make_tmap_bf16(&tmB, d_w, 2, dw, sw, bw));
+    const uint64_t dc[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    const uint64_t sc[1] = {static_cast<uint64_t>(ldx) * 4};
+    const uint32_t bc[2] = {32, 32};
+    B200X_TRY(make_tmap(&tmC, d_x, 4, 2, dc, sc, bc, 1));
+    GemmParams p{M, N, K, d_x, ldx, B200X_GEMM_OUT_F32_RESID, d_bias, 0, nullptr, 0, 0, 0, nullptr, reverse ? 1 : 0};
+    GemmLnTail q{d_x, ldx, d_gamma, d_beta, eps, reinterpret_cast<__nv_bfloat16*>(d_h), ldh};
+    return launch_gemm2_resid_ln<BN>(tmA, tmB, tmC, p, q, static_cast<cudaStream_t>(stream));
 }

@@ -34,6 +34,10 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// all state spaces: generic-proxy writes to GLOBAL memory that a later TMA load (async proxy) reads
+__device__ __forceinline__ void fence_proxy_async_all() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
@@ -190,6 +194,26 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     // default (.release.cta) semantics, like CUTLASS' ClusterBarrier::arrive(cta_id): the data this signal orders is TMEM
     // (fenced with tcgen05.fence::before_thread_sync); a .release.cluster arrive costs a MEMBAR.ALL.GPU per call
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// cluster-scope release arrive / acquire wait: the signalled data is SHARED MEMORY written by the arriving CTA's threads
+// (made visible to the async proxy with fence.proxy.async first) and consumed by tcgen05.mma.cta_group::2 of the leader
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 26)) __trap();
+    }
 }
 // TMA load into THIS CTA's shared memory whose completion bytes are credited to an mbarrier of the pair's leader CTA
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {

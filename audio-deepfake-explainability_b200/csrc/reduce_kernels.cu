@@ -6,6 +6,7 @@
 //   * band_map_kernel ......... FBP rows: map[(freqs>=low)&(freqs<=high), :] += delta (src/dsp_band_ops.py:652-653)
 //   * rank_kernel ............. stable ranking of windows by key (Python sorted() semantics incl. ties)
 #include "common.h"
+#include "layernorm_rows.cuh"
 
 namespace b200x {
 
@@ -24,6 +25,19 @@ layernorm_kernel(const float* __restrict__ x, int rows, int D, const float* __re
     const float* gamma = second ? gamma_b : gamma_a;
     const float* beta = second ? beta_b : beta_a;
     const float4* src = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+    if constexpr (VPL <= 3) {
+        // widths up to 384: the shared row routine (the LayerNorm tail of the residual GEMM runs the same code)
+        float4 v[1][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[0][i] = i < VPL ? src[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        layernorm_rows<1>(v, VPL, 1.0f / static_cast<float>(D), eps, gamma, beta, lane, [&](int, int i, float4 o) {
+            if (out_bf16 != nullptr)
+                reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * D)[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+            else
+                reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * D)[lane + 32 * i] = o;
+        });
+        return;
+    }
     float4 v[VPL];
     float s = 0.f;
 #pragma unroll
@@ -53,11 +67,7 @@ layernorm_kernel(const float* __restrict__ x, int rows, int D, const float* __re
         o.z = (v[i].z - mean) * rstd * g.z + b.z;
         o.w = (v[i].w - mean) * rstd * g.w + b.w;
         if (out_bf16 != nullptr) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
-            uint2 w;
-            w.x = *reinterpret_cast<uint32_t*>(&p0);
-            w.y = *reinterpret_cast<uint32_t*>(&p1);
-            reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * D)[lane + 32 * i] = w;
+            reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * D)[lane + 32 * i] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
         } else {
             reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * D)[lane + 32 * i] = o;
         }

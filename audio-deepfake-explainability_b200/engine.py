@@ -324,6 +324,10 @@ class Engine:
         """Alternate the row / tile traversal direction between consecutive kernels of the forward (L2 reuse; default on)."""
         _lib.check(self.lib.b200x_engine_set_alternate(self._h, int(enable)), "set_alternate")
 
+    def set_fused_layernorm(self, enable: bool) -> None:
+        """LayerNorm as a tail of the residual GEMM before it (default) or as a separate pass; results are bit-identical."""
+        _lib.check(self.lib.b200x_engine_set_fused_layernorm(self._h, int(enable)), "set_fused_layernorm")
+
     def set_graphs(self, enable: bool) -> None:
         """Replay the per-chunk classifier forward from a CUDA graph (default) or launch kernel by kernel."""
         _lib.check(self.lib.b200x_engine_set_graphs(self._h, int(enable)), "set_graphs")

@@ -156,6 +156,16 @@ int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, i
                     int ldc, int out_mode, const float* d_bias, int act_gelu, const float* d_resid, const float* d_pe,
                     int group_in, int group_out, int group_off, int reverse, void* stream);
 
+/* x += A . W^T + bias on the fp32 residual stream, then h = bf16(LayerNorm(x) * gamma + beta): a residual projection of a
+ * pre-norm encoder block (attention proj, fc2) fused with the LayerNorm that FOLLOWS it (x + sublayer(x) then nn.LayerNorm in
+ * the third-party encoder block reached through src/sonics_api.py:259-271).  Each CTA normalises its rows right after its
+ * reduce-adds completed, from L2: the residual stream is not read back from HBM.  Same arithmetic as b200x_gemm_bf16
+ * (B200X_GEMM_OUT_F32_RESID) followed by b200x_layernorm, bit for bit.  N = LayerNorm width (multiple of 128, <= 384);
+ * d_a bf16 [M][lda], d_w bf16 [N][ldw], d_x fp32 [M][ldx] (in/out), d_h bf16 [M][ldh] (out). */
+int b200x_gemm_resid_ln_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, float* d_x, int ldx,
+                             const float* d_bias, const float* d_gamma, const float* d_beta, float eps, void* d_h, int ldh,
+                             int reverse, void* stream);
+
 /* fused softmax(Q K^T / sqrt(d)) V for d_qkv bf16 [copies*tokens][3*heads*64] = [q|k|v]; d_out bf16
  * [copies*tokens][heads*64].  (F.scaled_dot_product_attention inside the third-party encoder) */
 int b200x_attention(const void* d_qkv, void* d_out, int copies, int tokens, int heads, int head_dim, int reverse,
@@ -316,6 +326,9 @@ int b200x_engine_set_alternate(b200x_engine* e, int enable);
 /* The classifier forward of a chunk is replayed from a CUDA graph once its shape has been seen twice (default on);
  * 0 = always launch kernel by kernel.  Results are identical either way. */
 int b200x_engine_set_graphs(b200x_engine* e, int enable);
+/* LayerNorm_1 of block l+1 as a tail of block l's fc2 GEMM (b200x_gemm_resid_ln_bf16, default on) or as a separate pass.
+ * Results are bit-identical either way. */
+int b200x_engine_set_fused_layernorm(b200x_engine* e, int enable);
 int b200x_engine_get_timing(b200x_engine* e, double* ms_per_class, int64_t* launches_per_class);
 void* b200x_engine_stream(b200x_engine* e);
 int b200x_engine_synchronize(b200x_engine* e);

@@ -123,3 +123,51 @@ def test_cta_pair_kernel_is_deterministic_and_direction_independent(M, N, K, bn,
     assert (first - ref).abs().max().item() <= tol
     for i in range(12):
         assert torch.equal(once(i & 1), first)
+
+
+@pytest.mark.parametrize("M,N,K,bias", [
+    (300, 384, 384, True),              # ragged, fewer row tiles than CTA pairs
+    (2 * 1376 + 77, 384, 384, True),    # attention projection
+    (2 * 1376 + 77, 384, 1040, True),   # fc2: padded hidden width, K not a multiple of 64
+    (20 * 1376, 384, 384, False),       # 108 row tiles over 74 pairs: x_ready / ln_done are reused
+    (64 * 1376, 384, 1040, True),       # 344 row tiles: 4-5 per CTA pair
+    (5 * 1376, 256, 384, True),         # LayerNorm width 256 (two vectors per lane)
+])
+def test_residual_gemm_with_layernorm_tail_is_bit_identical_to_the_two_kernels(M, N, K, bias):
+    """b200x_gemm_resid_ln_bf16 (x += a.W^T + b by TMA reduce-add, then LayerNorm of the CTA's own rows from L2) against
+    b200x_gemm_bf16(RESID) followed by b200x_layernorm on the same inputs: x and h carry the same bits, in both traversal
+    directions, launch after launch."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).cuda() if bias else None
+    x0 = (torch.randn(M, N, generator=g) * 1.7 + 0.3).cuda()
+    gamma = (1.0 + 0.1 * torch.randn(N, generator=g)).cuda()
+    beta = (0.1 * torch.randn(N, generator=g)).cuda()
+    x_ref = x0.clone()
+    ok(lib().b200x_gemm_bf16(P(a), K, P(w), K, M, N, K, 192, P(x_ref), N, OUT_RESID, P(b), 0, P(x_ref), P(None), 0, 0, 0, 0, P(None)))
+    h_ref = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    ok(lib().b200x_layernorm(P(x_ref), M, N, P(gamma), P(beta), P(None), P(None), 0, 0, 1e-6, P(h_ref), P(None), 0, P(None)))
+    # pin the pair itself against plain torch
+    want = x0 + a.float() @ w.float().T + (b if bias else 0.0)
+    assert (x_ref - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item())
+    hw = torch.nn.functional.layer_norm(x_ref, (N,), gamma, beta, 1e-6)
+    assert (h_ref.float() - hw).abs().max().item() <= 2e-2 * max(1.0, hw.abs().max().item())
+    for i in range(6):
+        x = x0.clone()
+        h = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ok(lib().b200x_gemm_resid_ln_bf16(P(a), K, P(w), K, M, N, K, P(x), N, P(b), P(gamma), P(beta), 1e-6, P(h), N, i & 1, P(None)))
+        torch.cuda.synchronize()
+        assert torch.equal(x, x_ref), f"launch {i}: x differs by {(x - x_ref).abs().max().item()}"
+        assert torch.equal(h, h_ref), f"launch {i}: h differs by {(h.float() - h_ref.float()).abs().max().item()}"
+
+
+def test_residual_gemm_with_layernorm_tail_rejects_bad_arguments():
+    a = torch.zeros(128, 384, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(512, 384, dtype=torch.bfloat16, device="cuda")
+    x = torch.zeros(128, 512, device="cuda")
+    h = torch.zeros(128, 512, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(RuntimeError):       # LayerNorm width 512 > 384: a row tile no longer fits two column tiles of 192
+        ok(lib().b200x_gemm_resid_ln_bf16(P(a), 384, P(w), 384, 128, 512, 384, P(x), 512, P(None), P(x), P(x), 1e-6, P(h), 512, 0, P(None)))
+    with pytest.raises(RuntimeError):       # NULL LayerNorm parameters
+        ok(lib().b200x_gemm_resid_ln_bf16(P(a), 384, P(w), 384, 128, 384, 384, P(x), 512, P(None), P(None), P(None), 1e-6, P(h), 512, 0, P(None)))

@@ -71,6 +71,10 @@ total += timeit(lambda: _lib.check(lib.b200x_attention(P(qkv), P(att), copies, T
 total += timeit(lambda: gemm(att, D, w_proj, D, M, D, D, 192, x, D, 1, b_d, 0, x), flops=2 * M * D * D, name="gemm proj  N=384  K=384  resid")
 total += timeit(lambda: gemm(h, D, w_fc1, D, M, HP, D, 208, hid, HP, 0, b_h, 1, None), flops=2 * M * D * HP, name="gemm fc1   N=1040 K=384  gelu")
 total += timeit(lambda: gemm(hid, HP, w_fc2, HP, M, D, HP, 192, x, D, 1, b_d, 0, x), flops=2 * M * D * HP, name="gemm fc2   N=384  K=1040 resid")
+timeit(lambda: _lib.check(lib.b200x_gemm_resid_ln_bf16(P(att), D, P(w_proj), D, M, D, D, P(x), D, P(b_d), P(gam), P(bet), 1e-5, P(h), D, 0, P(None))),
+       flops=2 * M * D * D, name="gemm proj + LayerNorm tail")
+timeit(lambda: _lib.check(lib.b200x_gemm_resid_ln_bf16(P(hid), HP, P(w_fc2), HP, M, D, HP, P(x), D, P(b_d), P(gam), P(bet), 1e-5, P(h), D, 0, P(None))),
+       flops=2 * M * D * HP, name="gemm fc2 + LayerNorm tail")
 layer_flops = 2 * M * D * (3 * D + D + 2 * 1025) + 4 * copies * H * T * T * 64
 print(f"{'one encoder layer (sum)':34s} {total:9.1f} us  {layer_flops / total / 1e6:8.1f} TFLOP/s  -> {12 * total / copies:7.1f} us/eval for 12 layers")
 
