@@ -28,7 +28,7 @@ constexpr int DSP_WARPS = 4;                    // warps per CTA for the FFT ker
 constexpr int DSP_THREADS = DSP_WARPS * 32;
 constexpr int DSP_SMEM = (DSP_WARPS * FFT_TILE + FFT_TWIDDLE) * 8;
 constexpr int ISTFT_ROW = 1026;                 // float2 elements copied per spectrogram row (1025 bins + 1: 16-byte multiple)
-constexpr int MEL_SEGS_PER_LANE = 5;            // ceil((128 + 1) / 32)
+constexpr int MEL_MAX_SLOTS = 96;               // bins per lane of the filterbank walk (33 on average at 128 mels)
 constexpr int MEL_SMEM = DSP_SMEM + DSP_WARPS * 2048 * 4 + DSP_WARPS * 8;   // + one staged 2048-sample frame and one mbarrier per warp
 constexpr int ISTFT_SMEM = DSP_SMEM + DSP_WARPS * 2 * ISTFT_ROW * 8 + DSP_WARPS * 2 * 8;
 
@@ -317,10 +317,13 @@ struct MelParams {
     int n_frames;
     int n_mels;                // <= 128, multiple of 32
     // triangular filterbank by SEGMENTS between consecutive centre frequencies: a bin of segment j feeds filter j with its
-    // rising weight (.x) and filter j - 1 with its falling weight (.y), so mel[m] = U[m] + D[m + 1] with two sums per segment
-    const int* seg_start;      // [n_mels + 2] first bin of segment j (segment n_mels + 1 = end sentinel)
-    const float2* seg_weights; // [NBIN] (rising, falling) weight of every bin
-    const int* lane_segments;  // [32][MEL_SEGS_PER_LANE] segments summed by each lane (balanced by width, -1 = none)
+    // rising weight (.x) and filter j - 1 with its falling weight (.y), so mel[m] = U[m] + D[m + 1] with two sums per segment.
+    // Every lane owns a CONTIGUOUS run of whole (non-empty) segments, balanced by width; its bins are "slots" 0 .. mel_slots - 1.
+    const float2* lane_weights; // [mel_slots][32] (rising, falling) weight of slot i of lane l (slot-major: one coalesced 256-byte
+                                // load per slot); the sign bit of .x marks the LAST bin of a segment; (+0, 0) past the lane's run
+    const int2* lane_info;      // [32] (first bin, first compacted segment id) of each lane
+    const int2* filter_segs;    // [n_mels] compacted ids of the segments whose U / D sums make up filter m (-1 = empty segment)
+    int mel_slots;              // multiple of 8
     float amin;
     float* db;                 // [copies][db_frames][n_mels]; row (t - ma) when frame_range is given
     float* cta_max;            // [copies][gridDim.x]
@@ -357,6 +360,8 @@ mel_db_kernel(MelParams p) {
     const LaneTrig trig{};      // unused: this kernel runs at 128 registers / four CTAs per SM, where the table loads of the
                                 // window and the unpack twiddles measured faster (662 us vs 782 us per 64 sparse copies) than computing them
     float vmax = -INFINITY;
+    const int2 lane_run = __ldg(&p.lane_info[lane]);
+    const int lane_bin0 = lane_run.x, lane_seg0 = lane_run.y;
     int f_lo = 0, f_hi = p.n_frames;
     if (p.frame_range != nullptr) { f_lo = p.frame_range[2 * copy]; f_hi = p.frame_range[2 * copy + 1]; }
     const int f_begin = f_lo + blockIdx.x * p.frames_per_cta;
@@ -438,29 +443,42 @@ mel_db_kernel(MelParams p) {
         if (lane == 0) pw[1024] = xn.x * xn.x;
         __syncwarp();
         float* out = p.db + (static_cast<long long>(copy) * p.db_frames + (t - f_lo)) * p.n_mels;
-        // filterbank: every lane sums its (width-balanced) segments, two accumulators per segment; the per-filter serial
-        // loop this replaces made the lane with the widest filters run ~80 dependent load + FMA steps per frame
+        // filterbank: every lane walks its contiguous run of bins once.  The weights of a slot come from one coalesced load,
+        // all loads of a batch of eight slots are independent of the sums, and a segment's (U, D) pair is flushed when the
+        // sign-bit flag says its last bin has been added - the per-segment loops this replaces (variable trip counts, one
+        // lane-scattered weight load per step) held 47 % of the kernel's stall samples on their dependent loads.
+        // Same additions in the same order as before: results are bit-identical.
         float* segU = pw + 1056;
         float* segD = segU + 160;
-#pragma unroll
-        for (int sidx = 0; sidx < MEL_SEGS_PER_LANE; ++sidx) {
-            const int j = __ldg(&p.lane_segments[lane * MEL_SEGS_PER_LANE + sidx]);
-            if (j < 0) continue;
-            const int kb = __ldg(&p.seg_start[j]), ke = __ldg(&p.seg_start[j + 1]);
+        {
+            int j = lane_seg0;
             float au = 0.f, ad = 0.f;
-#pragma unroll 4
-            for (int k = kb; k < ke; ++k) {
-                const float2 w = __ldg(&p.seg_weights[k]);
-                const float x = pw[k];
-                au = fmaf(w.x, x, au);
-                ad = fmaf(w.y, x, ad);
+            for (int base = 0; base < p.mel_slots; base += 8) {
+                float2 w[8];
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    w[u] = __ldg(&p.lane_weights[(base + u) * 32 + lane]);
+                    x[u] = pw[min(lane_bin0 + base + u, NBIN - 1)];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    au = fmaf(fabsf(w[u].x), x[u], au);
+                    ad = fmaf(w[u].y, x[u], ad);
+                    if (__float_as_int(w[u].x) < 0) {          // last bin of segment j
+                        segU[j] = au;
+                        segD[j] = ad;
+                        au = 0.f;
+                        ad = 0.f;
+                        ++j;
+                    }
+                }
             }
-            segU[j] = au;
-            segD[j] = ad;
         }
         __syncwarp();
         for (int f = lane; f < p.n_mels; f += 32) {
-            const float acc = segU[f] + segD[f + 1];
+            const int2 m = __ldg(&p.filter_segs[f]);
+            const float acc = (m.x >= 0 ? segU[m.x] : 0.f) + (m.y >= 0 ? segD[m.y] : 0.f);
             const float d = 10.0f * log10f(fmaxf(acc, p.amin));
             out[f] = d;
             vmax = fmaxf(vmax, d);
@@ -795,9 +813,9 @@ extern "C" int b200x_istft_masked_tracks(const void* d_spec, int spec_stride, in
 namespace b200x {
 // HTK mel filterbank, torchaudio.functional.melscale_fbanks(norm=None, mel_scale='htk') restated; sparse rows.
 struct MelBank {
-    int n_mels = 0;
-    int *d_seg_start = nullptr, *d_lane_segments = nullptr;
-    float2* d_seg_weights = nullptr;
+    int n_mels = 0, mel_slots = 0;
+    float2* d_lane_weights = nullptr;
+    int2 *d_lane_info = nullptr, *d_filter_segs = nullptr;
 };
 struct MelBankSlot { MelBank bank; double key[3] = {0, 0, 0}; };
 static std::map<int, MelBankSlot> g_banks;                 // one filterbank per DEVICE (its pointers are device allocations)
@@ -846,25 +864,56 @@ static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_ma
     }
     for (int k = NBIN - 1; k >= 0; --k) seg_start[seg_of[k]] = k;
     for (int j = n_seg - 1; j >= 0; --j) seg_start[j] = std::min(seg_start[j], seg_start[j + 1]);   // empty segments
-    // longest-first greedy assignment of segments to lanes
-    std::vector<int> order(n_seg), load(32, 0), used(32, 0), lane_segs(32 * MEL_SEGS_PER_LANE, -1);
-    for (int j = 0; j < n_seg; ++j) order[j] = j;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seg_start[a + 1] - seg_start[a] > seg_start[b + 1] - seg_start[b]; });
-    for (int j : order) {
-        int best = -1;
-        for (int l = 0; l < 32; ++l)
-            if (used[l] < MEL_SEGS_PER_LANE && (best < 0 || load[l] < load[best])) best = l;
-        if (best < 0) return set_error(B200X_ERR_INVALID, "mel bank: %d segments do not fit 32 x %d lane slots", n_seg, MEL_SEGS_PER_LANE);
-        lane_segs[best * MEL_SEGS_PER_LANE + used[best]++] = j;
-        load[best] += seg_start[j + 1] - seg_start[j] + 2;
+    // compact the non-empty segments and cut them into 32 contiguous runs of whole segments with the smallest possible
+    // longest run (binary search on the cap, greedy fill)
+    std::vector<int> compact(n_seg, -1), seg_ids;
+    for (int j = 0; j < n_seg; ++j)
+        if (seg_start[j + 1] > seg_start[j]) { compact[j] = static_cast<int>(seg_ids.size()); seg_ids.push_back(j); }
+    const int n_ne = static_cast<int>(seg_ids.size());
+    auto width = [&](int c) { return seg_start[seg_ids[c] + 1] - seg_start[seg_ids[c]]; };
+    auto runs_needed = [&](int cap) {
+        int runs = 1, fill = 0;
+        for (int c = 0; c < n_ne; ++c) {
+            if (width(c) > cap) return 1 << 30;
+            if (fill + width(c) > cap) { ++runs; fill = 0; }
+            fill += width(c);
+        }
+        return runs;
+    };
+    int lo = 1, hi = NBIN;
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (runs_needed(mid) <= 32) hi = mid; else lo = mid + 1;
     }
-    if (g_bank.d_seg_start) { cudaFree(g_bank.d_seg_start); cudaFree(g_bank.d_lane_segments); cudaFree(g_bank.d_seg_weights); }
-    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_seg_start, seg_start.size() * sizeof(int)));
-    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_lane_segments, lane_segs.size() * sizeof(int)));
-    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_seg_weights, NBIN * sizeof(float2)));
-    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_seg_start, seg_start.data(), seg_start.size() * sizeof(int), cudaMemcpyHostToDevice));
-    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_lane_segments, lane_segs.data(), lane_segs.size() * sizeof(int), cudaMemcpyHostToDevice));
-    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_seg_weights, w.data(), NBIN * sizeof(float2), cudaMemcpyHostToDevice));
+    const int cap = lo;
+    const int slots = (cap + 7) / 8 * 8;
+    if (slots > MEL_MAX_SLOTS) return set_error(B200X_ERR_INVALID, "mel bank: a lane would walk %d bins (limit %d)", cap, MEL_MAX_SLOTS);
+    std::vector<int2> lane_info(32, make_int2(NBIN - 1, n_ne));
+    std::vector<float2> lane_w(static_cast<size_t>(slots) * 32, make_float2(0.f, 0.f));
+    {
+        int lane = 0, fill = 0;
+        for (int c = 0; c < n_ne; ++c) {
+            if (fill + width(c) > cap) { ++lane; fill = 0; }
+            const int j = seg_ids[c];
+            if (fill == 0) lane_info[lane] = make_int2(seg_start[j], c);
+            for (int k = seg_start[j]; k < seg_start[j + 1]; ++k, ++fill) {
+                float2 v = w[k];
+                if (k == seg_start[j + 1] - 1) v.x = -v.x;            // flag: last bin of the segment (-0.0f for a zero weight)
+                lane_w[static_cast<size_t>(fill) * 32 + lane] = v;
+            }
+        }
+    }
+    // contiguity check: a lane's slots must be consecutive bins (segments are, and runs are made of consecutive segments)
+    std::vector<int2> filt(n_mels);
+    for (int f = 0; f < n_mels; ++f) filt[f] = make_int2(compact[f], compact[f + 1]);
+    if (g_bank.d_lane_weights) { cudaFree(g_bank.d_lane_weights); cudaFree(g_bank.d_lane_info); cudaFree(g_bank.d_filter_segs); }
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_lane_weights, lane_w.size() * sizeof(float2)));
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_lane_info, lane_info.size() * sizeof(int2)));
+    B200X_CUDA_TRY(cudaMalloc(&g_bank.d_filter_segs, filt.size() * sizeof(int2)));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_lane_weights, lane_w.data(), lane_w.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_lane_info, lane_info.data(), lane_info.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    B200X_CUDA_TRY(cudaMemcpy(g_bank.d_filter_segs, filt.data(), filt.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    g_bank.mel_slots = slots;
     g_bank.n_mels = n_mels;
     g_bank_key[0] = sample_rate; g_bank_key[1] = f_min; g_bank_key[2] = f_max;
     *out = g_bank;
@@ -904,7 +953,7 @@ extern "C" int b200x_mel_db_ref(const float* d_y, int64_t y_stride, int64_t n_sa
     MelParams p;
     p.y = d_y; p.y_stride = y_stride; p.n_samples = n_samples; p.sumsq = d_sumsq; p.ref_rms = ref_rms; p.ref_rms_arr = d_ref_rms_per_copy; p.rms_count = rms_count;
     p.n_frames = 1 + static_cast<int>(n_samples / HOP); p.n_mels = n_mels;
-    p.seg_start = g_bank.d_seg_start; p.seg_weights = g_bank.d_seg_weights; p.lane_segments = g_bank.d_lane_segments;
+    p.lane_weights = g_bank.d_lane_weights; p.lane_info = g_bank.d_lane_info; p.filter_segs = g_bank.d_filter_segs; p.mel_slots = g_bank.mel_slots;
     p.amin = static_cast<float>(amin); p.db = d_db; p.cta_max = d_cta_max; p.frames_per_cta = b200x_mel_frames_per_cta();
     p.db_frames = db_frames; p.frame_range = d_frame_range;
     const int span = d_frame_range ? std::min(p.n_frames, std::max(1, max_range_frames)) : p.n_frames;
