@@ -29,7 +29,11 @@ constexpr int DSP_THREADS = DSP_WARPS * 32;
 constexpr int DSP_SMEM = (DSP_WARPS * FFT_TILE + FFT_TWIDDLE) * 8;
 constexpr int ISTFT_ROW = 1026;                 // float2 elements copied per spectrogram row (1025 bins + 1: 16-byte multiple)
 constexpr int MEL_MAX_SLOTS = 96;               // bins per lane of the filterbank walk (33 on average at 128 mels)
+#ifdef B200X_MEL_NO_STAGE
+constexpr int MEL_SMEM = DSP_SMEM + DSP_WARPS * 8;
+#else
 constexpr int MEL_SMEM = DSP_SMEM + DSP_WARPS * 2048 * 4 + DSP_WARPS * 8;   // + one staged 2048-sample frame and one mbarrier per warp
+#endif
 constexpr int ISTFT_SMEM = DSP_SMEM + DSP_WARPS * 2 * ISTFT_ROW * 8 + DSP_WARPS * 2 * 8;
 
 __global__ void init_tables_kernel() {
@@ -154,7 +158,7 @@ struct IstftParams {
 #define B200X_ISTFT_MIN_CTAS 1
 #endif
 #ifndef B200X_MEL_MIN_CTAS
-#define B200X_MEL_MIN_CTAS 3
+#define B200X_MEL_MIN_CTAS 4
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(DSP_THREADS, B200X_ISTFT_MIN_CTAS)
@@ -332,7 +336,8 @@ struct MelParams {
     const int* frame_range;    // optional [copies][2] = [ma, mb): only these frames are computed
 };
 
-__global__ void __launch_bounds__(DSP_THREADS, B200X_MEL_MIN_CTAS)      // 3: 168 registers, 74 KB of shared memory: three CTAs per SM
+__global__ void __launch_bounds__(DSP_THREADS, B200X_MEL_MIN_CTAS)      // 4 -> 128 registers (no spills); 74 KB of shared memory still means three CTAs per SM,
+                                                                        // but the tighter allocation measured 2-3 % faster (profiles/r02_k_dsp_variants.txt)
 mel_db_kernel(MelParams p) {
     extern __shared__ __align__(16) float2 dsp_smem[];
     __shared__ float s_max[DSP_WARPS];
@@ -357,8 +362,8 @@ mel_db_kernel(MelParams p) {
         const double ref = p.ref_rms_arr != nullptr ? p.ref_rms_arr[copy] : p.ref_rms;
         if (!(r_x < 1e-8) && ref >= 0.0) gain = static_cast<float>(ref / r_x);
     }
-    const LaneTrig trig{};      // unused: this kernel runs at 128 registers / four CTAs per SM, where the table loads of the
-                                // window and the unpack twiddles measured faster (662 us vs 782 us per 64 sparse copies) than computing them
+    const LaneTrig trig{};      // unused: here the table loads of the window and the unpack twiddles measured faster
+                                // (662 us vs 782 us per 64 sparse copies) than computing them
     float vmax = -INFINITY;
     const int2 lane_run = __ldg(&p.lane_info[lane]);
     const int lane_bin0 = lane_run.x, lane_seg0 = lane_run.y;
@@ -370,8 +375,16 @@ mel_db_kernel(MelParams p) {
     // per warp: the copy of the warp's NEXT frame is issued as soon as the current one sits in registers and lands during
     // the FFT, so the load stage no longer waits on L2 latency.  Edge frames (reflect padding) take the direct path.
     float* fbuf = reinterpret_cast<float*>(dsp_smem + DSP_WARPS * FFT_TILE + FFT_TWIDDLE) + warp * NFFT;
+#ifdef B200X_MEL_NO_STAGE
+    uint64_t* fbar = reinterpret_cast<uint64_t*>(dsp_smem + DSP_WARPS * FFT_TILE + FFT_TWIDDLE) + warp;
+#else
     uint64_t* fbar = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(dsp_smem + DSP_WARPS * FFT_TILE + FFT_TWIDDLE) + DSP_WARPS * NFFT) + warp;
+#endif
+#ifdef B200X_MEL_NO_STAGE
+    const bool can_stage = false;
+#else
     const bool can_stage = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+#endif
     auto interior_of = [&](int t) {
         const long long b = static_cast<long long>(t) * HOP - NFFT / 2;
         return b >= 0 && b + NFFT <= p.n_samples;
