@@ -121,6 +121,42 @@ def test_mel_db_matches_torchaudio():
     assert torch.allclose(cmax.amax(dim=1).cpu(), ref.amax(dim=(1, 2)), atol=1e-3)
 
 
+@pytest.mark.parametrize("sample_rate,n_mels,f_min,f_max", [
+    (44100, 128, 0.0, 22050.0),      # the reference's shipped sampling rate
+    (16000, 64, 20.0, 7600.0),       # fewer, wider filters; band edges inside the spectrum
+    (22050, 32, 0.0, 11025.0),       # one filter per lane: the widest segments (every lane walks ~ 33 bins)
+    (16000, 96, 0.0, 4000.0),        # f_max at half Nyquist: the upper half of the bins carries no weight
+    (8000, 128, 0.0, 4000.0),        # narrow filters: empty segments at the low end (two centre frequencies inside one bin)
+])
+def test_mel_filterbank_geometries_match_torchaudio(sample_rate, n_mels, f_min, f_max):
+    """The filterbank walk (contiguous runs of whole segments per lane, sign-bit flush, compacted non-empty segments) against
+    torchaudio's dense HTK filterbank for geometries other than the classifier's own."""
+    import dataclasses
+
+    cfg = dataclasses.replace(ALPHA_120S, sample_rate=sample_rate, n_mels=n_mels, f_min=f_min, f_max=f_max)
+    ys = np.stack([_track(6.0, "SUNO"), 0.3 * _track(6.0, "REAL")])
+    n = ys.shape[1]
+    buf = torch.zeros(2, n + 8, device="cuda")
+    buf[:, :n] = torch.from_numpy(ys).cuda()
+    n_frames = 1 + n // 512
+    n_cta = -(-n_frames // lib().b200x_mel_frames_per_cta())
+    db = torch.full((2, n_frames, n_mels), float("nan"), device="cuda")
+    cmax = torch.zeros(2, n_cta, device="cuda")
+    ok(lib().b200x_mel_db(P(buf), buf.shape[1], n, 2, sample_rate, n_mels, f_min, f_max, cfg.amin, P(None), 0.0, n, P(db), n_frames,
+                          P(cmax), P(None), 0, P(None)))
+    power = dsp.mel_frontend(torch.from_numpy(ys), cfg, "power")
+    ref = 10.0 * torch.log10(torch.clamp(power, min=cfg.amin)).transpose(1, 2)
+    got = db.cpu()
+    assert torch.isfinite(got).all()
+    live = ref > ref.amax(dim=(1, 2), keepdim=True) - 80.0
+    assert (got - ref)[live].abs().max().item() < 2e-3
+    # and back to the classifier's own bank (the per-device table is rebuilt on a geometry change)
+    db2, _, _, _ = _gpu_mel_db(buf, n)
+    ref2 = 10.0 * torch.log10(torch.clamp(dsp.mel_frontend(torch.from_numpy(ys), ALPHA_120S, "power"), min=ALPHA_120S.amin)).transpose(1, 2)
+    live2 = ref2 > ref2.amax(dim=(1, 2), keepdim=True) - 80.0
+    assert (db2.cpu() - ref2)[live2].abs().max().item() < 2e-3
+
+
 def test_mel_normalize_resize_matches_oracle():
     cfg = ALPHA_120S
     ys = np.stack([_track(12.0, "SUNO_PRO"), _track(12.0, "ElevenLabs")])
