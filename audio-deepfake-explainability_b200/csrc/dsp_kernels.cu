@@ -896,12 +896,24 @@ static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_ma
     for (int k = NBIN - 1; k >= 0; --k) seg_start[seg_of[k]] = k;
     for (int j = n_seg - 1; j >= 0; --j) seg_start[j] = std::min(seg_start[j], seg_start[j + 1]);   // empty segments
     // compact the non-empty segments and cut them into 32 contiguous runs of whole segments with the smallest possible
-    // longest run (binary search on the cap, greedy fill)
+    // longest run (binary search on the cap, greedy fill).  Bins that carry no weight at the two ends of the spectrum (below
+    // f_min in the first segment, above f_max in the last one - half of the spectrum when f_max is half Nyquist) are trimmed:
+    // they sit at the start of the first run / the end of the last run, so every run stays a contiguous range of bins.
+    std::vector<int> eff_start(seg_start.begin(), seg_start.end() - 1), eff_end(seg_start.begin() + 1, seg_start.end());
+    auto silent = [&](int k) { return w[k].x == 0.f && w[k].y == 0.f; };
+    for (int j = 0; j < n_seg; ++j) {                     // leading silent bins of the spectrum
+        while (eff_start[j] < eff_end[j] && silent(eff_start[j])) ++eff_start[j];
+        if (eff_start[j] < eff_end[j]) break;
+    }
+    for (int j = n_seg - 1; j >= 0; --j) {                // trailing silent bins
+        while (eff_end[j] > eff_start[j] && silent(eff_end[j] - 1)) --eff_end[j];
+        if (eff_end[j] > eff_start[j]) break;
+    }
     std::vector<int> compact(n_seg, -1), seg_ids;
     for (int j = 0; j < n_seg; ++j)
-        if (seg_start[j + 1] > seg_start[j]) { compact[j] = static_cast<int>(seg_ids.size()); seg_ids.push_back(j); }
+        if (eff_end[j] > eff_start[j]) { compact[j] = static_cast<int>(seg_ids.size()); seg_ids.push_back(j); }
     const int n_ne = static_cast<int>(seg_ids.size());
-    auto width = [&](int c) { return seg_start[seg_ids[c] + 1] - seg_start[seg_ids[c]]; };
+    auto width = [&](int c) { return eff_end[seg_ids[c]] - eff_start[seg_ids[c]]; };
     auto runs_needed = [&](int cap) {
         int runs = 1, fill = 0;
         for (int c = 0; c < n_ne; ++c) {
@@ -926,10 +938,10 @@ static int ensure_melbank(int sample_rate, int n_mels, double f_min, double f_ma
         for (int c = 0; c < n_ne; ++c) {
             if (fill + width(c) > cap) { ++lane; fill = 0; }
             const int j = seg_ids[c];
-            if (fill == 0) lane_info[lane] = make_int2(seg_start[j], c);
-            for (int k = seg_start[j]; k < seg_start[j + 1]; ++k, ++fill) {
+            if (fill == 0) lane_info[lane] = make_int2(eff_start[j], c);
+            for (int k = eff_start[j]; k < eff_end[j]; ++k, ++fill) {
                 float2 v = w[k];
-                if (k == seg_start[j + 1] - 1) v.x = -v.x;            // flag: last bin of the segment (-0.0f for a zero weight)
+                if (k == eff_end[j] - 1) v.x = -v.x;                 // flag: last bin of the segment (-0.0f for a zero weight)
                 lane_w[static_cast<size_t>(fill) * 32 + lane] = v;
             }
         }
