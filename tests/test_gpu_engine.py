@@ -165,3 +165,24 @@ def test_graph_replay_is_bit_identical_to_eager_launches(eng):
     for r in runs:
         assert np.array_equal(r, eager)
     assert np.array_equal(eng.predict(np.stack([y, y[::-1].copy()])), np.concatenate([eng.predict(y)[None], eng.predict(y[::-1].copy())[None]]))
+
+
+def test_layernorm_tail_is_bit_identical_to_the_separate_pass(eng):
+    """fc2 + LayerNorm tail (b200x_gemm_resid_ln_bf16, the default) against residual GEMM followed by the LayerNorm pass: the
+    same bits through twelve blocks, eager and from the replayed graph, for a ragged chunk (11 copies in chunks of 4)."""
+    y = synth.synth_track("UDIO", 5, 16000, 6.0)
+    eng.set_track(y)
+    n_freq, n_time = eng.track_shape()
+    wins = grid.occlusion_windows(n_freq, n_time, 64, 32, 25.0, 12.5)[:11]
+    try:
+        eng.set_fused_layernorm(False)
+        separate = [eng.occlusion_sweep(wins, 0.0) for _ in range(3)]
+        p_sep = eng.predict(y)
+        eng.set_fused_layernorm(True)
+        fused = [eng.occlusion_sweep(wins, 0.0) for _ in range(3)]
+        p_fused = eng.predict(y)
+    finally:
+        eng.set_fused_layernorm(True)
+    for a in separate + fused:
+        assert np.array_equal(a, separate[0])
+    assert p_sep == p_fused
