@@ -150,12 +150,16 @@ class FrequencyBandPerturbation:
             importance_map[rows, :] += d
         return FBDResult(importance_map, mel_host.power_to_db_refmax(S), orig_prob, sig, S, batch)
 
-    def compute_importance_batch(self, signals: Sequence[np.ndarray], component_name: str = "mixture") -> List[FBDResult]:
+    def compute_importance_batch(self, signals: Sequence[np.ndarray], component_name: str = "mixture",
+                                 materialize_maps: bool = False) -> List[FBDResult]:
         """``_compute_component_importance`` for a batch of equal-length signals in shared launches (BASELINE configs[2]:
         64 tracks x the high_resolution bank).  The reference handles one file at a time (:529-666); here the band copies
         of as many tracks as fit a chunk go through one iSTFT launch and one classifier forward, with results identical
         to the per-track call.  ``S`` / ``spectrogram_db`` are not materialised (30 MB per track on the host) - ask the
-        per-track method for them."""
+        per-track method for them.  ``importance_map`` is a read-only broadcast view of the map's single distinct column
+        (``grid.band_map_view``; same values, same shape and dtype as the per-track method's array - a third of the batch's
+        wall time was the device -> host copy of 64 x 30.8 MB of repeated columns); ``materialize_maps=True`` returns the
+        device-built writable arrays instead."""
         if not signals:
             return []
         waves = np.stack([np.ascontiguousarray(np.asarray(s, dtype=np.float32)) for s in signals])
@@ -169,7 +173,10 @@ class FrequencyBandPerturbation:
             deltas = [float(orig_prob - float(p)) for p in probs[i]]
             batch = [{"component": component_name, "low": float(lo), "high": float(hi), "importance": d}
                      for (lo, hi), d in zip(self.bands, deltas)]
-            importance_map = eng.band_map(rows, np.asarray(deltas, dtype=np.float64))
+            if materialize_maps:
+                importance_map = eng.band_map(rows, np.asarray(deltas, dtype=np.float64))
+            else:
+                importance_map = grid.band_map_view(rows, deltas, self.n_fft // 2 + 1, 1 + waves.shape[1] // self.hop_length)
             out.append(FBDResult(importance_map, None, orig_prob, waves[i], None, batch))
         return out
 

@@ -124,6 +124,17 @@ def band_bin_ranges(bands: Sequence[Tuple[float, float]], sr: float, n_fft: int)
     return out
 
 
+def band_map_view(band_rows: np.ndarray, deltas: Sequence[float], n_freq: int, n_time: int) -> np.ndarray:
+    """The FBP importance map ``map[(freqs >= low) & (freqs <= high), :] += delta`` (src/dsp_band_ops.py:652-653) as a READ-ONLY
+    broadcast view: every column of that map is the same ``[n_freq]`` float64 vector (the additions run in band order, like
+    the reference's), so the ``[n_freq, n_time]`` array (30.8 MB per 120 s track) never has to be produced or copied.
+    ``np.array(view)`` materialises a writable copy."""
+    col = np.zeros(n_freq, dtype=np.float64)
+    for (r0, r1), d in zip(np.asarray(band_rows).reshape(-1, 2), deltas):
+        col[int(r0):int(r1)] += np.float64(d)
+    return np.broadcast_to(col[:, None], (n_freq, n_time))
+
+
 def importance_type(v: float) -> str:
     return "POSITIVE" if v > 0 else "NEGATIVE" if v < 0 else "NEUTRAL"
 

@@ -482,13 +482,16 @@ def fbp64(ctx: Ctx, steps: int, warmup: int, n_tracks: int = 64):
         gains = grid.band_gain_table(bands, SR, 2048, 0.25, "rel", 0.2, 5.0, 500.0, 0.0).astype(np.float32)
         rows = grid.band_bin_ranges(bands, SR, 2048)
         out = {}
-        for normalize in (False, True):
+        n_freq, n_time = 1025, 1 + waves.shape[1] // 512
+        for normalize, materialize in ((False, False), (True, False), (False, True)):
             def step():
                 base, prob = eng.fbp_sweep_tracks(waves, gains, normalize)
                 delta = base.astype(np.float64)[:, None] - prob.astype(np.float64)
                 m = None
                 for d in delta:
-                    m = eng.band_map(rows, d)
+                    # the batch API's default: a read-only broadcast view of the map's one distinct column (host, band-order
+                    # float64 adds); materialize = the device-built [1025, n_time] float64 array read back per track
+                    m = eng.band_map(rows, d) if materialize else grid.band_map_view(rows, d, n_freq, n_time)
                 return m
             for _ in range(max(2, warmup)):
                 step()
@@ -500,11 +503,12 @@ def fbp64(ctx: Ctx, steps: int, warmup: int, n_tracks: int = 64):
             eng.synchronize()
             wall = ctx.max_over_ranks(1e3 * (time.perf_counter() - t0))
             evals = n_tracks * (len(bands) + 1) * steps
-            out[f"normalize_loudness={normalize}"] = {"value": evals / (wall * 1e-3), "unit": "evals/s", "ms_per_step": wall / steps,
-                                                       "evals_per_step": n_tracks * (len(bands) + 1),
-                                                       "gpu_launches": int(eng.launch_count - l0),
-                                                       "h2d_bytes_per_step": int(waves.nbytes + gains.nbytes),
-                                                       "d2h_bytes_per_step": int(len(waves) * (14 * 4 + 1025 * 3751 * 8))}
+            key = "materialized_maps" if materialize else f"normalize_loudness={normalize}"
+            out[key] = {"value": evals / (wall * 1e-3), "unit": "evals/s", "ms_per_step": wall / steps,
+                        "evals_per_step": n_tracks * (len(bands) + 1),
+                        "gpu_launches": int(eng.launch_count - l0),
+                        "h2d_bytes_per_step": int(waves.nbytes + gains.nbytes),
+                        "d2h_bytes_per_step": int(len(waves) * (14 * 4 + (n_freq * n_time * 8 if materialize else 0)))}
         return out
     finally:
         eng.close()
@@ -725,8 +729,10 @@ def run_engine(args):
             f = fbp64(ctx, 1, 2)
             s = stems1000(ctx, 1, 1)
             line["workloads"] = {"fbp64": dict(f["normalize_loudness=False"], workload="configs[2]: 13-band high_resolution FBP, 64 tracks, "
-                                               "batch-of-tracks entry point, host buffers (end to end)",
-                                               normalize_loudness_true=f["normalize_loudness=True"]),
+                                               "batch-of-tracks entry point, host buffers (end to end); importance maps as read-only "
+                                               "broadcast views of their one distinct column (the batch API's default)",
+                                               normalize_loudness_true=f["normalize_loudness=True"],
+                                               materialized_maps=f["materialized_maps"]),
                                  "stems1000": dict(s, workload="configs[4]: 1000 stem-mask recombinations of 4 stems, host buffers (end to end)")}
     if roofline is not None:
         line["roofline"] = roofline

@@ -77,3 +77,25 @@ def test_shard_range():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(ws - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_band_map_view_equals_the_reference_accumulation():
+    """grid.band_map_view (read-only broadcast of the map's one distinct column) against the reference's
+    map[(freqs >= low) & (freqs <= high), :] += delta (src/dsp_band_ops.py:652-653), overlapping bands included."""
+    import numpy as np
+    from audio_deepfake_explainability_b200 import grid
+
+    for preset, sr in (("high_resolution", 16000), ("high_resolution", 44100), ("default", 16000)):
+        if preset not in grid.FREQUENCY_BAND_PRESETS:
+            continue
+        bands = list(grid.FREQUENCY_BAND_PRESETS[preset]) + [(100.0, 900.0)]        # one overlapping band
+        rows = grid.band_bin_ranges(bands, sr, 2048)
+        d = np.random.default_rng(len(bands) + sr).normal(size=len(bands))
+        ref = np.zeros((1025, 37))
+        freqs = grid.fft_frequencies(sr, 2048)
+        for (lo, hi), dd in zip(bands, d):
+            ref[(freqs >= lo) & (freqs <= hi), :] += dd
+        view = grid.band_map_view(rows, d, 1025, 37)
+        assert view.shape == ref.shape and view.dtype == ref.dtype and np.array_equal(view, ref)
+        assert not view.flags.writeable
+        assert np.array_equal(np.array(view), ref) and np.array(view).flags.writeable
