@@ -531,6 +531,197 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 
+// ------------------------------------------------------------------------------------------------ A-stationary CTA-pair GEMM
+// For wide outputs of a narrow K (QKV: N = 1152 = 6 column tiles, K = 384): the pair kernel above re-reads the 128 x K row tile
+// of A from L2 once per column tile, and the L2 -> SM operand traffic is what paces it.  Here a CTA keeps its row tile in
+// shared memory (K <= 384: six 16 KB k-blocks, loaded ONCE per row tile by a third single-thread role, k-block by k-block as
+// the last column tile of the previous row tile releases them) and sweeps all column tiles of W over it:
+//   * a stage of the ring is only the B half tile (12 KB), so the ring is 7-8 stages deep and covers the ~3 k-cycle L2 -> SM
+//     round trip (in-kernel counters: with 4 stages the issuer waited 390 cycles per k-step for weights);
+//   * the pairs walk the column tiles in ROTATED orders - in lockstep all 74 pairs pull the same 24 KB weight tile out of the
+//     same few L2 slices at the same time;
+//   * the epilogue warps make do with one output slab each.
+// Same MMAs in the same order as gemm2_bf16_tn_kernel: results are bit-identical.  Measured at 229 copies (profiles/
+// r02_g_gemm_ln_astationary.txt, debug = 1 rows): 252-265 us against 267-270 us (1.05-1.11 PFLOP/s).
+constexpr int GEMM_AS_MAX_KB = 6;
+constexpr int GEMM_AS_W_TMA_A = 2 + GEMM_EPI_WARPS;
+constexpr int GEMM_AS_THREADS = 32 * (GEMM_AS_W_TMA_A + 1);
+
+template <int BN>
+struct GemmAsSmem {
+    static constexpr int A_KB_BYTES = GEMM_BM * GEMM_BK * 2;                  // 16 KB per k-block
+    static constexpr int A_BYTES = GEMM_AS_MAX_KB * A_KB_BYTES;               // 96 KB
+    static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;
+    static constexpr int EPI_WARP_BYTES = GEMM_SLAB_BYTES;
+    static constexpr int STAGES_FIT = (232448 - 1024 - 512 - A_BYTES - GEMM_EPI_WARPS * EPI_WARP_BYTES) / B_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int B_OFFSET = A_BYTES;
+    static constexpr int EPI_OFFSET = B_OFFSET + STAGES * B_BYTES;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + GEMM_EPI_WARPS * EPI_WARP_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+    static_assert(B_BYTES % 1024 == 0, "B half tile must keep 1024-byte alignment for the 128B swizzle");
+    static_assert(STAGES >= 4 && TOTAL <= 232448, "shared memory budget exceeded");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_AS_THREADS, 1)
+gemm2_astat_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCtail, GemmParams p) {
+    using L = GemmAsSmem<BN>;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+    constexpr int STAGES = L::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* a_full = tempty_bar + 2;                   // [6] k-block kb of the row tile has landed in BOTH CTAs (leader's copy)
+    uint64_t* a_empty = a_full + GEMM_AS_MAX_KB;         // [6] per CTA: the row tile's last MMAs on k-block kb have retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + GEMM_AS_MAX_KB);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+    const int n_rot = pair % n_tiles;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
+        }
+        for (int s = 0; s < GEMM_AS_MAX_KB; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer: weight half tiles only
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mt = pair; mt < m_tiles; mt += n_pairs) {
+                for (int j = 0; j < n_tiles; ++j) {
+                    const int n_blk = (j + n_rot) % n_tiles;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::B_BYTES);
+                        const uint32_t leader_full = mapa_shared(&full_bar[stage], 0);
+                        tma_load_2d_pair(smem + L::B_OFFSET + stage * L::B_BYTES, &tmB, leader_full, kb * GEMM_BK,
+                                         n_blk * BN + static_cast<int>(rank) * (BN / 2));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, false);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0, tphase = 0;
+            for (int mt = pair; mt < m_tiles; mt += n_pairs, tphase ^= 1) {
+                for (int j = 0; j < n_tiles; ++j) {
+                    mbar_wait(&tempty_bar[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * BN;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        if (j == 0) mbar_wait(&a_full[kb], tphase);              // both CTAs' k-block has landed
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + kb * L::A_KB_BYTES);
+                        const uint32_t b_addr = smem_u32(smem + L::B_OFFSET + stage * L::B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                            umma_ss_pair(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_pair(&empty_bar[stage]);
+                        if (j == n_tiles - 1) umma_commit_pair(&a_empty[kb]);    // last reader of this k-block: refill it
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_pair(&tfull_bar[as]);
+                    if (++as == 2) { as = 0; aphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < GEMM_AS_W_TMA_A) {
+        // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        uint8_t* slab = smem + L::EPI_OFFSET + (warp - 2) * L::EPI_WARP_BYTES;
+        int as = 0, buf = 0, tile_parity = 0;
+        uint32_t aphase = 0;
+        const uint32_t leader_tempty0 = mapa_shared(&tempty_bar[0], 0), leader_tempty1 = mapa_shared(&tempty_bar[1], 0);
+        for (int mt = pair; mt < m_tiles; mt += n_pairs) {
+            const int m_blk = p.reverse ? m_tiles - 1 - mt : mt;
+            for (int j = 0; j < n_tiles; ++j, ++tile_parity) {
+                const int n_blk = (j + n_rot) % n_tiles;
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const int m_warp = m_blk * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32;
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
+                epilogue_store_tile<BN, 1>(p, tmC, tmCtail, slab, buf, t_row, m_warp, n_blk, half ^ (tile_parity & 1), lane);
+                tc_fence_before();
+                __syncwarp();
+                if (elect_one()) mbar_arrive_cluster(as == 0 ? leader_tempty0 : leader_tempty1);
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+        bulk_wait<0>();
+    } else {
+        // ------------------------------------------------------------------ TMA-A: the stationary row tile, k-block by k-block
+        if (elect_one()) {
+            int it = 0;
+            for (int mt = pair; mt < m_tiles; mt += n_pairs, ++it) {
+                const int m_blk = p.reverse ? m_tiles - 1 - mt : mt;
+                const int row = m_blk * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (it > 0) mbar_wait(&a_empty[kb], (it - 1) & 1);       // the previous row tile no longer reads this k-block
+                    if (rank == 0) mbar_expect_tx(&a_full[kb], 2 * L::A_KB_BYTES);
+                    tma_load_2d_pair(smem + kb * L::A_KB_BYTES, &tmA, mapa_shared(&a_full[kb], 0), kb * GEMM_BK, row);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+static int launch_gemm2_astat(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
+                              const GemmParams& p, cudaStream_t stream) {
+    using L = GemmAsSmem<BN>;
+    int num_sms = 0;
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(gemm2_astat_bf16_tn_kernel<BN>), L::TOTAL));
+    B200X_TRY(device_sm_count(&num_sms));
+    const int pairs = std::min(ceil_div(p.M, 2 * GEMM_BM), num_sms / 2);
+    gemm2_astat_bf16_tn_kernel<BN><<<2 * pairs, GEMM_AS_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmCtail, p);
+    B200X_CUDA_TRY(cudaGetLastError());
+    return B200X_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ residual GEMM + LayerNorm tail
 // x += A . W^T + bias (fp32 residual stream, TMA reduce-add as above), then h = LayerNorm(x) in bf16 for the projection that
 // follows (attention proj -> LN2 -> fc1; fc2 -> next block's LN1 -> QKV).  The separate LayerNorm pass read the 484 MB
@@ -860,6 +1051,16 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
     }
     GemmParams p{M, N, K, d_out, ldc, out_mode, d_bias, act_gelu, d_pe, group_in, group_out, group_off, nullptr, (pair && reverse) ? 1 : 0};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // wide bf16 output of a narrow K (QKV, fc1): the A-stationary kernel, from four row tiles per CTA pair
+    // upwards (its work unit is a whole row tile: below that the last, partly filled wave costs more than the saved operand
+    // traffic gains); QKV 244 vs 267 us at 229 copies, 75.0 vs 78.2 us at 64; fc1 (epilogue-bound) 293 vs 297 us
+    // (profiles/r02_p_kernel_bench.txt)
+    int num_sms_d = 0;
+    B200X_TRY(device_sm_count(&num_sms_d));
+    const bool astat = pair && out_mode == B200X_GEMM_OUT_BF16 && (block_n == 192 || block_n == 208) && K % GEMM_BK == 0 &&
+                       K <= GEMM_AS_MAX_KB * GEMM_BK && N >= 4 * block_n && ceil_div(M, 2 * GEMM_BM) >= 4 * (num_sms_d / 2);
+    if (astat && block_n == 192) return launch_gemm2_astat<192>(tmA, tmB, tmC, tmCtail, p, s);
+    if (astat && block_n == 208) return launch_gemm2_astat<208>(tmA, tmB, tmC, tmCtail, p, s);
     if (pair) {
         switch (block_n) {
             case 192: return launch_gemm2<192>(tmA, tmB, tmC, tmCtail, p, s);
@@ -905,4 +1106,33 @@ extern "C" int b200x_gemm_resid_ln_bf16(const void* d_a, int lda, const void* d_
     GemmParams p{M, N, K, d_x, ldx, B200X_GEMM_OUT_F32_RESID, d_bias, 0, nullptr, 0, 0, 0, nullptr, reverse ? 1 : 0};
     GemmLnTail q{d_x, ldx, d_gamma, d_beta, eps, reinterpret_cast<__nv_bfloat16*>(d_h), ldh};
     return launch_gemm2_resid_ln<BN>(tmA, tmB, tmC, p, q, static_cast<cudaStream_t>(stream));
+}
+
+/* The A-stationary kernel on its own (b200x_gemm_bf16 picks it for wide bf16 outputs of a narrow K at large M): bf16 output,
+ * optional bias / GELU, K a multiple of 64 up to 384, column tiles of 192 or 208. */
+extern "C" int b200x_gemm_bf16_astationary(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n,
+                                           void* d_out, int ldc, const float* d_bias, int act_gelu, int reverse, void* stream) {
+    B200X_REQUIRE(block_n == 192 || block_n == 208, "gemm_astationary: block_n %d unsupported (192 / 208)", block_n);
+    B200X_REQUIRE(d_a && d_w && d_out, "gemm_astationary: NULL argument");
+    B200X_REQUIRE(M > 0 && N > 0 && N % 16 == 0, "gemm_astationary: bad problem M=%d N=%d", M, N);
+    B200X_REQUIRE(K % GEMM_BK == 0 && K >= GEMM_BK && K <= GEMM_AS_MAX_KB * GEMM_BK, "gemm_astationary: K=%d must be a multiple of 64 up to 384", K);
+    B200X_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm_astationary: leading dimensions must be multiples of 8");
+    B200X_REQUIRE(d_bias == nullptr || (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0, "gemm_astationary: bias not 16-byte aligned");
+    CUtensorMap tmA, tmB, tmC, tmCtail;
+    const uint64_t da[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t sa[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t ba[2] = {GEMM_BK, GEMM_BM};
+    B200X_TRY(make_tmap_bf16(&tmA, d_a, 2, da, sa, ba));
+    const uint64_t dw[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t sw[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t bw[2] = {GEMM_BK, static_cast<uint32_t>(block_n / 2)};
+    B200X_TRY(make_tmap_bf16(&tmB, d_w, 2, dw, sw, bw));
+    const uint64_t dc[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    const uint64_t sc[1] = {static_cast<uint64_t>(ldc) * 2};
+    const uint32_t bc[2] = {64, 32}, bt[2] = {16, 32};
+    B200X_TRY(make_tmap(&tmC, d_out, 2, 2, dc, sc, bc, 1));
+    B200X_TRY(make_tmap(&tmCtail, d_out, 2, 2, dc, sc, bt, 0));
+    GemmParams p{M, N, K, d_out, ldc, B200X_GEMM_OUT_BF16, d_bias, act_gelu, nullptr, 0, 0, 0, nullptr, reverse ? 1 : 0};
+    if (block_n == 208) return launch_gemm2_astat<208>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream));
+    return launch_gemm2_astat<192>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream));
 }

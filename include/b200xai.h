@@ -156,6 +156,14 @@ int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, i
                     int ldc, int out_mode, const float* d_bias, int act_gelu, const float* d_resid, const float* d_pe,
                     int group_in, int group_out, int group_off, int reverse, void* stream);
 
+/* The A-stationary CTA-pair kernel that b200x_gemm_bf16 selects for wide bf16 outputs of a narrow K at large M (the QKV
+ * projection, nn.Linear(384, 1152) of the third-party encoder block): a CTA keeps its 128 x K row tile of A in shared memory and
+ * sweeps every 192-column tile of W over it, so A crosses L2 -> SM once instead of once per column tile.  Same MMAs in the same
+ * order as the pair kernel: bit-identical results.  bf16 output, optional bias / GELU; K a multiple of 64 up to 384; block_n 192
+ * or 208. */
+int b200x_gemm_bf16_astationary(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n, void* d_out,
+                                int ldc, const float* d_bias, int act_gelu, int reverse, void* stream);
+
 /* x += A . W^T + bias on the fp32 residual stream, then h = bf16(LayerNorm(x) * gamma + beta): a residual projection of a
  * pre-norm encoder block (attention proj, fc2) fused with the LayerNorm that FOLLOWS it (x + sublayer(x) then nn.LayerNorm in
  * the third-party encoder block reached through src/sonics_api.py:259-271).  Each CTA normalises its rows right after its

@@ -171,3 +171,33 @@ def test_residual_gemm_with_layernorm_tail_rejects_bad_arguments():
         ok(lib().b200x_gemm_resid_ln_bf16(P(a), 384, P(w), 384, 128, 512, 384, P(x), 512, P(None), P(x), P(x), 1e-6, P(h), 512, 0, P(None)))
     with pytest.raises(RuntimeError):       # NULL LayerNorm parameters
         ok(lib().b200x_gemm_resid_ln_bf16(P(a), 384, P(w), 384, 128, 384, 384, P(x), 512, P(None), P(None), P(None), 1e-6, P(h), 512, 0, P(None)))
+
+
+@pytest.mark.parametrize("M,N,K,bn,bias,gelu", [
+    (300, 1152, 384, 192, False, False),            # one ragged row tile
+    (2 * 1376 + 77, 1152, 384, 192, True, False),   # QKV with bias, ragged
+    (40 * 1376, 1152, 384, 192, False, False),      # 215 row tiles over 74 pairs: the stationary k-blocks are refilled
+    (9 * 1376, 768, 256, 192, True, False),         # four column tiles, four k-blocks
+    (9 * 1376 + 5, 1040, 384, 208, True, True),     # fc1 shape: GELU epilogue, 16-column tail group
+])
+def test_a_stationary_gemm_is_bit_identical_to_the_pair_kernel(M, N, K, bn, bias, gelu):
+    """b200x_gemm_bf16_astationary (row tile of A resident in shared memory, rotated column-tile order, deep weight ring) against
+    the CTA-pair kernel behind b200x_gemm_bf16 at the same shapes: same bits, both traversal directions, launch after launch."""
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).cuda() if bias else None
+    ref = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    ok(lib().b200x_gemm_bf16(P(a), K, P(w), K, min(M, 4 * 73 * 256), N, K, bn, P(ref), N, OUT_BF16, P(b), int(gelu), P(None), P(None), 0, 0, 0, 0, P(None)))
+    if M > 4 * 73 * 256:                # keep the reference on the pair kernel (the dispatcher switches at 4 row tiles per pair)
+        m0 = 4 * 73 * 256
+        ok(lib().b200x_gemm_bf16(P(a[m0:]), K, P(w), K, M - m0, N, K, bn, P(ref[m0:]), N, OUT_BF16, P(b), int(gelu), P(None), P(None), 0, 0, 0, 0, P(None)))
+    want = a.float() @ w.float().T + (b if bias else 0.0)
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    assert (ref.float() - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    for i in range(6):
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ok(lib().b200x_gemm_bf16_astationary(P(a), K, P(w), K, M, N, K, bn, P(out), N, P(b), int(gelu), i & 1, P(None)))
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), f"launch {i}: {(out.float() - ref.float()).abs().max().item()}"

@@ -75,6 +75,10 @@ timeit(lambda: _lib.check(lib.b200x_gemm_resid_ln_bf16(P(att), D, P(w_proj), D, 
        flops=2 * M * D * D, name="gemm proj + LayerNorm tail")
 timeit(lambda: _lib.check(lib.b200x_gemm_resid_ln_bf16(P(hid), HP, P(w_fc2), HP, M, D, HP, P(x), D, P(b_d), P(gam), P(bet), 1e-5, P(h), D, 0, P(None))),
        flops=2 * M * D * HP, name="gemm fc2 + LayerNorm tail")
+timeit(lambda: _lib.check(lib.b200x_gemm_bf16_astationary(P(h), D, P(w_qkv), D, M, 3 * D, D, 192, P(qkv), 3 * D, P(None), 0, 0, P(None))),
+       flops=2 * M * D * 3 * D, name="gemm qkv A-stationary")
+timeit(lambda: _lib.check(lib.b200x_gemm_bf16_astationary(P(h), D, P(w_fc1), D, M, HP, D, 208, P(hid), HP, P(b_h), 1, 0, P(None))),
+       flops=2 * M * D * HP, name="gemm fc1 A-stationary (gelu)")
 layer_flops = 2 * M * D * (3 * D + D + 2 * 1025) + 4 * copies * H * T * T * 64
 print(f"{'one encoder layer (sum)':34s} {total:9.1f} us  {layer_flops / total / 1e6:8.1f} TFLOP/s  -> {12 * total / copies:7.1f} us/eval for 12 layers")
 
