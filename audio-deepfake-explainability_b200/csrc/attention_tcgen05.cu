@@ -22,7 +22,8 @@
 // The qkv buffer is the QKV GEMM output [copies * tokens, 3 * heads * 64] = [q | k | v] (timm reshape order).
 //
 // Variants that were built, measured and rejected (two tiles per CTA, split rows, 64-key tiles, software-pipelined loads,
-// a persistent ping-pong kernel with one softmax warp set alternating between two tiles) live in tools/variants/ with their
+// a persistent ping-pong kernel with one softmax warp set alternating between two tiles, 64-key tiles with three CTAs per SM
+// and P beside S) live in tools/variants/ with their
 // numbers in DESIGN.md 3.2; none of them is part of this library.
 #include "common.h"
 #include "ptx.cuh"
