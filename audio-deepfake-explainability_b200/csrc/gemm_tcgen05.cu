@@ -739,7 +739,8 @@ static int launch_gemm2_astat(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 // = A + reduce-add RMW + 0.45 GB) - lines produced by TMA reduce-adds are not retained in L2 (an evict_last cache hint on the
 // reduction changes nothing), so the K = 384 projection, already at 5.7 TB/s, only gets longer.  The engine therefore uses
 // the tail behind fc2 (K = 1040, tensor-bound with HBM headroom) and keeps the separate LayerNorm pass behind proj.
-constexpr int GEMM_RLN_LN_WARPS = 8;
+constexpr int GEMM_RLN_LN_WARPS = 8;                  // 4 warps: fc2 + tail 469 us, 16 warps (72 registers): 385-417 us, 8: 377 us
+                                                      // (profiles/r02_h_gemm_resid_ln.txt, last block)
 // warp roles: the SM's warp arbiter prefers HIGHER warp ids, and a TMA producer / MMA issuer that loses its issue slots to the
 // eight busy LayerNorm warps delays every tcgen05.mma - so the single-thread roles sit on top, the LayerNorm tail at the bottom
 constexpr int GEMM_RLN_W_EPI = GEMM_RLN_LN_WARPS;                  // 8..15 (quarter = warp & 3 still names the TMEM lane quarter)
