@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200x_mix_stems": (C.c_int, [VP, C.c_int64, C.c_int, VP, C.c_int, VP, C.c_int64, VP]),
     "b200x_gemm_bf16": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_int, C.c_int,
                                   VP, C.c_int, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP]),
+    "b200x_gemm_tokens_mmajor": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, C.c_int, VP, C.c_int, VP, C.c_int, C.c_int, VP]),
     "b200x_gemm_bf16_astationary": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_int, VP, C.c_int, C.c_int, VP]),
     "b200x_gemm_resid_ln_bf16": (C.c_int, [VP, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, C.c_int, VP, VP, VP, C.c_float, VP, C.c_int,
                                            C.c_int, VP]),

@@ -643,8 +643,9 @@ mel_resize_kernel(ResizeParams p) {
         const float o3 = lam0 * ((fmaxf(a.w, fl) - mean) * inv) + lam1 * ((fmaxf(b.w, fl) - mean) * inv);
         const uint2 w = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
         *reinterpret_cast<uint2*>(p.img_t + (static_cast<long long>(copy) * p.out_t + j) * p.n_mels + f) = w;
-        *reinterpret_cast<uint2*>(&s_tile[jj][f]) = w;
+        if (p.img_f != nullptr) *reinterpret_cast<uint2*>(&s_tile[jj][f]) = w;
     }
+    if (p.img_f == nullptr) return;                      // the consumer reads the [time][mel] image through an M-major descriptor
     __syncthreads();
     // transposed copy [mel][time]: one thread = four consecutive output frames of one mel bin (8-byte stores when aligned)
     const bool vec_ok = (p.ld_f % 4 == 0) && (j0 + 64 <= p.out_t);

@@ -115,6 +115,7 @@ struct b200x_engine {
     uint64_t graph_clock = 0;
     static constexpr size_t max_graphs = 16;   // least-recently-used shapes beyond this are destroyed (tracks of many lengths)
     bool use_graphs = true;
+    bool spectral_mmajor = false;   // n_mels == 128, f_clip == 1: no transposed image (b200x_gemm_tokens_mmajor)
     bool fuse_ln = true;       // LayerNorm as a tail of the residual GEMM before it (gemm_resid_ln) instead of a pass of its own
     DevBuf prob_chunk, logit_chunk, ranges_chunk;      // fixed addresses baked into the graphs
 
@@ -192,15 +193,22 @@ int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const dou
                                          c.n_mels, static_cast<float>(c.top_db), c.std_unbiased, c.norm_eps, c.input_temp_dim,
                                          d_ranges ? e->db_base.as<float>() : nullptr, e->base_pre.as<float>(),
                                          e->base_suf.as<float>(), d_ranges, e->partial.p, e->floor_v.as<float>(), e->img_t.p,
-                                         e->img_f.p, c.input_temp_dim, s));
+                                         e->spectral_mmajor ? nullptr : e->img_f.p, c.input_temp_dim, s));
     e->launches += 3;
     // tokenizers: temporal rows = t_clip consecutive time steps x n_mels; spectral rows = one mel row over time
     const int Kt = c.t_clip * c.input_spec_dim;
     TIMED(KC_GEMM, b200x_gemm_bf16(e->img_t.p, Kt, e->tok_t_w.p, Kt, copies * e->Tt, D, Kt, pick_block_n(D), e->x.p, D,
                               B200X_GEMM_OUT_F32_TOKEN, e->tok_t_b.as<float>(), 1, nullptr, e->pe_t.as<float>(), e->Tt, T, 0, 0, s));
-    TIMED(KC_GEMM, b200x_gemm_bf16(e->img_f.p, c.input_temp_dim, e->tok_s_w.p, c.input_temp_dim, copies * e->Ts, D,
-                              c.input_temp_dim, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_TOKEN, e->tok_s_b.as<float>(), 1,
-                              nullptr, e->pe_s.as<float>(), e->Ts, T, e->Tt, 0, s));
+    if (e->spectral_mmajor) {
+        // 128 mel rows = one 128-row MMA tile per copy: the spectral tokenizer reads the [time][mel] image through an M-major
+        // operand descriptor; the transposed [mel][time] copy (img_f) is never written
+        TIMED(KC_GEMM, b200x_gemm_tokens_mmajor(e->img_t.p, copies, c.input_temp_dim, e->tok_s_w.p, c.input_temp_dim, D, e->x.as<float>(), D,
+                                           e->tok_s_b.as<float>(), 1, e->pe_s.as<float>(), T, e->Tt, s));
+    } else {
+        TIMED(KC_GEMM, b200x_gemm_bf16(e->img_f.p, c.input_temp_dim, e->tok_s_w.p, c.input_temp_dim, copies * e->Ts, D,
+                                  c.input_temp_dim, pick_block_n(D), e->x.p, D, B200X_GEMM_OUT_F32_TOKEN, e->tok_s_b.as<float>(), 1,
+                                  nullptr, e->pe_s.as<float>(), e->Ts, T, e->Tt, 0, s));
+    }
     e->launches += 2;
     if (c.pre_norm) {
         TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, e->np_t_g.as<float>(), e->np_t_b.as<float>(), e->np_s_g.as<float>(),
@@ -376,7 +384,8 @@ extern "C" int b200x_engine_create(const b200x_model_config* cfg, int copies_per
     A(e->partial, static_cast<size_t>(C) * 32 * 2 * sizeof(double));
     A(e->floor_v, static_cast<size_t>(C) * sizeof(float));
     A(e->img_t, static_cast<size_t>(C) * cfg->input_temp_dim * cfg->n_mels * 2);
-    A(e->img_f, static_cast<size_t>(C) * cfg->n_mels * cfg->input_temp_dim * 2);
+    e->spectral_mmajor = cfg->n_mels == 128 && cfg->input_spec_dim == 128 && cfg->f_clip == 1 && e->Ts == 128;
+    if (!e->spectral_mmajor) A(e->img_f, static_cast<size_t>(C) * cfg->n_mels * cfg->input_temp_dim * 2);
     A(e->x, M * D * sizeof(float));
     A(e->h, M * D * 2);
     A(e->qkv, M * 3 * D * 2);
@@ -1290,6 +1299,7 @@ extern "C" int b200x_engine_debug_buffer(b200x_engine* e, const char* name, void
     else if (n == "prob") b = &e->prob; else if (n == "logit") b = &e->logit; else if (n == "S") b = &e->S;
     else if (n == "wave") b = &e->wave;
     else return set_error(B200X_ERR_INVALID, "debug_buffer: unknown buffer '%s'", name);
+    if (b->p == nullptr) return set_error(B200X_ERR_STATE, "debug_buffer: '%s' is not materialised in this configuration", name);
     *d_ptr = b->p;
     if (bytes) *bytes = static_cast<int64_t>(b->bytes);
     return B200X_OK;

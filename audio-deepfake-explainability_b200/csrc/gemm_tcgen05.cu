@@ -41,6 +41,7 @@ struct GemmParams {
     int group_in, group_out, group_off;   // out_row = (m / group_in) * group_out + group_off + m % group_in
     long long* prof;      // diagnostic (usually null): per CTA {issuer wait on loads, wait on epilogue, issuer total, tiles}
     int reverse;          // walk the tile list from its end (L2 reuse of the producer kernel's last output, see runtime.cu)
+    int a_mmajor;         // single-CTA kernel only: A is [batch][K][128] (M-major: row tile m_blk = batch element, 3-D tensor map)
 };
 
 template <int BN>
@@ -259,7 +260,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    if (p.a_mmajor) {
+                        // M-major A: two [64 k][64 m] boxes (128-byte rows of 64 consecutive m), the m halves 8 KB apart
+                        tma_load_3d(sa, &tmA, &full_bar[stage], 0, kb * GEMM_BK, m_blk);
+                        tma_load_3d(sa + L::A_BYTES / 2, &tmA, &full_bar[stage], 64, kb * GEMM_BK, m_blk);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+                    }
                     tma_load_2d(sa + L::A_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -268,7 +275,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (elect_one()) {          // elect.sync: ptxas emits straight-line UTMALDG / UTCHMMA (no per-lane BRA.U.ANY loop)
-            constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, false);
+            const uint32_t idesc = p.a_mmajor ? make_idesc_bf16(GEMM_BM, BN, false, true) : make_idesc_bf16(GEMM_BM, BN, false);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -290,7 +297,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        // K-major A: 16 k = 32 bytes along the 128-byte row; M-major A: 16 k = 16 rows of 128 bytes, the two
+                        // 64-wide m blocks 8 KB apart (leading byte offset), 8-row swizzle groups 1 KB apart
+                        const uint64_t ad = p.a_mmajor ? make_smem_desc_sw128(a_addr + k * 2048, L::A_BYTES / 2, 1024)
+                                                       : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
                         umma_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
@@ -1136,4 +1146,27 @@ extern "C" int b200x_gemm_bf16_astationary(const void* d_a, int lda, const void*
     GemmParams p{M, N, K, d_out, ldc, B200X_GEMM_OUT_BF16, d_bias, act_gelu, nullptr, 0, 0, 0, nullptr, reverse ? 1 : 0};
     if (block_n == 208) return launch_gemm2_astat<208>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream));
     return launch_gemm2_astat<192>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream));
+}
+
+/* Token-mode GEMM whose A operand is M-major: d_img bf16 [batch][K][128] (one 128-row tile per batch element, rows = the
+ * contiguous index), out_row = b * group_out + group_off + m, out = act(A . W^T + bias) + pe[m].  The spectral tokenizer reads
+ * the [time][mel] image the temporal tokenizer uses, so the transposed [mel][time] copy never has to be written. */
+extern "C" int b200x_gemm_tokens_mmajor(const void* d_img, int batch, int K, const void* d_w, int ldw, int N, float* d_out, int ldc,
+                                        const float* d_bias, int act_gelu, const float* d_pe, int group_out, int group_off,
+                                        void* stream) {
+    B200X_REQUIRE(d_img && d_w && d_out && d_pe, "gemm_tokens_mmajor: NULL argument");
+    B200X_REQUIRE(batch > 0 && K > 0 && K % 8 == 0 && ldw % 8 == 0 && N > 0 && N % 4 == 0 && ldc % 4 == 0, "gemm_tokens_mmajor: bad sizes");
+    B200X_REQUIRE(d_bias == nullptr || (reinterpret_cast<uintptr_t>(d_bias) & 15) == 0, "gemm_tokens_mmajor: bias not 16-byte aligned");
+    constexpr int BN = 192;
+    CUtensorMap tmA, tmB;
+    const uint64_t da[3] = {GEMM_BM, static_cast<uint64_t>(K), static_cast<uint64_t>(batch)};
+    const uint64_t sa[2] = {GEMM_BM * 2, static_cast<uint64_t>(K) * GEMM_BM * 2};
+    const uint32_t ba[3] = {64, GEMM_BK, 1};
+    B200X_TRY(make_tmap_bf16(&tmA, d_img, 3, da, sa, ba));
+    const uint64_t dw[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t sw[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t bw[2] = {GEMM_BK, BN};
+    B200X_TRY(make_tmap_bf16(&tmB, d_w, 2, dw, sw, bw));
+    GemmParams p{batch * GEMM_BM, N, K, d_out, ldc, B200X_GEMM_OUT_F32_TOKEN, d_bias, act_gelu, d_pe, GEMM_BM, group_out, group_off, nullptr, 0, 1};
+    return launch_gemm<BN>(tmA, tmB, tmA, tmA, p, static_cast<cudaStream_t>(stream));
 }

@@ -265,8 +265,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 // Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation:
 //  [4,6) D format 1 = f32   [7,10) A format 1 = bf16   [10,13) B format 1 = bf16
 //  [15] A major (0 = K)     [16] B major (0 = K, 1 = MN)   [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, bool b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, bool b_mn_major, bool a_mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) |
+           ((M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]

@@ -108,7 +108,8 @@ int b200x_wave_rms(const float* d_waves, int64_t n_samples, int64_t stride, int 
 int b200x_mel_base_maxima(const float* d_db_base, int n_frames, int n_mels, float* d_premax, float* d_sufmax, void* stream);
 
 /* top_db clamp, (x-mean)/(std+eps), F.interpolate(bilinear) along time to out_t, bf16, in both tokenizer operand
- * layouts: d_img_t [copies][out_t][n_mels], d_img_f [copies][n_mels][ld_f].  d_partial: 32*copies double2 scratch.
+ * layouts: d_img_t [copies][out_t][n_mels], d_img_f [copies][n_mels][ld_f] (d_img_f may be NULL: the transposed copy is
+ * skipped).  d_partial: 32*copies double2 scratch.
  * With d_db_base (+ maxima + d_frame_range) frames outside [ma, mb) are read from the baseline spectrogram. */
 int b200x_mel_normalize_resize(const float* d_db, int db_frames, const float* d_cta_max, int n_cta_max, int copies,
                                int n_frames, int n_mels, float top_db, int unbiased, float eps, int out_t,
@@ -155,6 +156,13 @@ int b200x_gl_update(const void* d_rebuilt, const void* d_tprev, const float* d_m
 int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ldw, int M, int N, int K, int block_n, void* d_out,
                     int ldc, int out_mode, const float* d_bias, int act_gelu, const float* d_resid, const float* d_pe,
                     int group_in, int group_out, int group_off, int reverse, void* stream);
+
+/* Token-mode GEMM (B200X_GEMM_OUT_F32_TOKEN with group_in = 128) whose A operand is M-MAJOR: d_img bf16 [batch][K][128], row tile
+ * b = the 128 contiguous indices of batch element b; out_row = b * group_out + group_off + m; out = act(A . W^T + bias) + pe[m].
+ * The spectral tokenizer (Conv1d over the mel axis of the [mel][time] image in the third-party encoder) reads the [time][mel]
+ * image the temporal tokenizer uses through an M-major tcgen05 operand descriptor, so the transposed copy is never written. */
+int b200x_gemm_tokens_mmajor(const void* d_img, int batch, int K, const void* d_w, int ldw, int N, float* d_out, int ldc,
+                             const float* d_bias, int act_gelu, const float* d_pe, int group_out, int group_off, void* stream);
 
 /* The A-stationary CTA-pair kernel that b200x_gemm_bf16 selects for wide bf16 outputs of a narrow K at large M (the QKV
  * projection, nn.Linear(384, 1152) of the third-party encoder block): a CTA keeps its 128 x K row tile of A in shared memory and

@@ -201,3 +201,29 @@ def test_a_stationary_gemm_is_bit_identical_to_the_pair_kernel(M, N, K, bn, bias
         ok(lib().b200x_gemm_bf16_astationary(P(a), K, P(w), K, M, N, K, bn, P(out), N, P(b), int(gelu), i & 1, P(None)))
         torch.cuda.synchronize()
         assert torch.equal(out, ref), f"launch {i}: {(out.float() - ref.float()).abs().max().item()}"
+
+
+@pytest.mark.parametrize("batch,K,gelu", [(3, 3744, True), (2, 96, False), (5, 640, True)])
+def test_token_gemm_with_m_major_operand_matches_the_k_major_call(batch, K, gelu):
+    """b200x_gemm_tokens_mmajor reads A as [batch][K][128] through an M-major tcgen05 descriptor; the regular token-mode call
+    on the transposed copy [batch * 128][K] must give the same bits (same products, same accumulation order)."""
+    N, T, off = 384, 1376, 1248
+    g = torch.Generator(device="cpu").manual_seed(K)
+    img = torch.randn(batch, K, 128, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    pe = torch.randn(128, N, generator=g).cuda()
+    a_k = img.transpose(1, 2).contiguous().reshape(batch * 128, K)
+    ref = torch.zeros(batch * T, N, device="cuda")
+    ok(lib().b200x_gemm_bf16(P(a_k), K, P(w), K, batch * 128, N, K, 192, P(ref), N, OUT_TOKEN, P(b), int(gelu), P(None), P(pe), 128, T, off, 0, P(None)))
+    want = a_k.float() @ w.float().T + b
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    want = (want.reshape(batch, 128, N) + pe).reshape(batch * 128, N)
+    got_ref = ref.reshape(batch, T, N)[:, off:off + 128].reshape(batch * 128, N)
+    assert (got_ref - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item())
+    for _ in range(3):
+        out = torch.zeros(batch * T, N, device="cuda")
+        ok(lib().b200x_gemm_tokens_mmajor(P(img), batch, K, P(w), K, N, P(out), N, P(b), int(gelu), P(pe), T, off, P(None)))
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), (out - ref).abs().max().item()
