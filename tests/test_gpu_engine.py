@@ -186,3 +186,38 @@ def test_layernorm_tail_is_bit_identical_to_the_separate_pass(eng):
     for a in separate + fused:
         assert np.array_equal(a, separate[0])
     assert p_sep == p_fused
+
+
+@pytest.mark.parametrize("n_mels,embed_dim,heads", [(64, 384, 6), (96, 256, 4)])
+def test_other_classifier_geometries_match_oracle(n_mels, embed_dim, heads):
+    """Classifier configurations other than the alpha-120s default: n_mels != 128 takes the K-major spectral tokenizer with the
+    transposed image copy (the 128-mel default reads one image through an M-major operand), embed_dim 256 takes the LayerNorm
+    paths with two vectors per lane and the generic GEMM tile choices.  Tokenizer, every block and the logit against the oracle."""
+    import dataclasses
+
+    cfg = dataclasses.replace(CFG, n_mels=n_mels, input_spec_dim=n_mels, embed_dim=embed_dim, num_heads=heads, num_layers=3)
+    sd2 = random_state_dict(cfg, 3)
+    e = Engine(cfg, sd2, copies_per_chunk=3, max_samples=12 * 16000)
+    try:
+        ys = np.stack([synth.synth_track("SUNO", 1, 16000, 10.0), synth.synth_track("REAL", 2, 16000, 10.0)])
+        M = cfg.num_tokens
+        trace = torch.zeros(cfg.num_layers + 1, 2 * M, cfg.embed_dim, device="cuda")
+        e.set_trace(trace.data_ptr())
+        try:
+            prob, logit = e.predict(ys, return_logits=True)
+        finally:
+            e.set_trace(None)
+        t = torch.from_numpy(ys)
+        img = spectttra.resize(dsp.mel_frontend(t, cfg), cfg)
+        tok = spectttra.tokenize(img, sd2, cfg, "bf16")
+        _, layers = spectttra.encoder(tok, sd2, cfg, "bf16", return_all=True)
+        tr = trace.cpu().reshape(cfg.num_layers + 1, 2, M, cfg.embed_dim)
+        assert (tr[0] - tok).abs().max().item() < 6e-3
+        for l, ref in enumerate(layers):
+            assert (tr[l + 1] - ref).abs().max().item() < 3e-2 * max(1.0, ref.abs().max().item() / 4), l
+        ref_logit = spectttra.forward_logits(t, sd2, cfg, "fp32").numpy().reshape(-1)
+        assert np.abs(np.asarray(logit).reshape(-1) - ref_logit).max() < 1.5e-2
+        assert np.abs(np.asarray(prob).reshape(-1) - 1.0 / (1.0 + np.exp(-ref_logit))).max() < TOL
+        assert np.array_equal(np.asarray(prob).reshape(-1), np.array([e.predict(y) for y in ys]).reshape(-1))
+    finally:
+        e.close()
