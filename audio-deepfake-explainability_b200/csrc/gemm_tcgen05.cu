@@ -107,7 +107,7 @@ __device__ __forceinline__ void convert_columns(const uint32_t* r, uint32_t* w, 
 
 // bf16 / residual epilogue of one 128 x BN accumulator tile for one epilogue warp (lane quarter of TMEM, every other
 // column group): TMEM -> registers -> bias (+GELU) -> swizzled slab -> one TMA tensor store (or reduce-add) per slab.
-template <int BN, int NBUF = 2>
+template <int BN, int NBUF = 2, int GSTRIDE = 2>
 __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
                                                     uint8_t* slab, int& buf, uint32_t t_row, int m_warp, int n_blk, int half, int lane,
                                                     long long* pc = nullptr) {
@@ -117,7 +117,7 @@ __device__ __forceinline__ void epilogue_store_tile(const GemmParams& p, const C
         // column groups of 64 (one 128-byte bf16 row per thread); BN = 208 ends with a 16-column group
         constexpr int NG = (BN + 63) / 64;
 #pragma unroll 1
-        for (int g = half; g < NG; g += 2) {
+        for (int g = half; g < NG; g += GSTRIDE) {
             const int c = g * 64;
             const int n0 = n_blk * BN + c;
             const bool full = (c + 64 <= BN);
@@ -553,31 +553,37 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 //   * the epilogue warps make do with one output slab each.
 // Same MMAs in the same order as gemm2_bf16_tn_kernel: results are bit-identical.  Measured at 229 copies (profiles/
 // r02_g_gemm_ln_astationary.txt, debug = 1 rows): 252-265 us against 267-270 us (1.05-1.11 PFLOP/s).
+constexpr int B200X_FC1_EPI_WARPS = 12;   // fc1 (GELU epilogue): 271.5-272.4 us with 12 epilogue warps against 276.3-278.2 us with 8 (profiles/r02_x_fc1_epilogue_warps.txt)
 constexpr int GEMM_AS_MAX_KB = 6;
-constexpr int GEMM_AS_W_TMA_A = 2 + GEMM_EPI_WARPS;
-constexpr int GEMM_AS_THREADS = 32 * (GEMM_AS_W_TMA_A + 1);
+// EW = epilogue warps: 8 (two per TMEM lane quarter) or 12 (three per quarter, for the GELU epilogue of fc1, which is
+// bound by the epilogue's dependent chains: TMEM load -> erf-GELU -> pack -> slab -> TMA store)
+template <int EW> struct GemmAsRoles {
+    static constexpr int W_TMA_A = 2 + EW;
+    static constexpr int THREADS = 32 * (W_TMA_A + 1);
+};
 
-template <int BN>
+template <int BN, int EW>
 struct GemmAsSmem {
     static constexpr int A_KB_BYTES = GEMM_BM * GEMM_BK * 2;                  // 16 KB per k-block
     static constexpr int A_BYTES = GEMM_AS_MAX_KB * A_KB_BYTES;               // 96 KB
     static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;
     static constexpr int EPI_WARP_BYTES = GEMM_SLAB_BYTES;
-    static constexpr int STAGES_FIT = (232448 - 1024 - 512 - A_BYTES - GEMM_EPI_WARPS * EPI_WARP_BYTES) / B_BYTES;
+    static constexpr int STAGES_FIT = (232448 - 1024 - 512 - A_BYTES - EW * EPI_WARP_BYTES) / B_BYTES;
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr int B_OFFSET = A_BYTES;
     static constexpr int EPI_OFFSET = B_OFFSET + STAGES * B_BYTES;
-    static constexpr int BAR_OFFSET = EPI_OFFSET + GEMM_EPI_WARPS * EPI_WARP_BYTES;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + EW * EPI_WARP_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
     static_assert(B_BYTES % 1024 == 0, "B half tile must keep 1024-byte alignment for the 128B swizzle");
     static_assert(STAGES >= 4 && TOTAL <= 232448, "shared memory budget exceeded");
 };
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_AS_THREADS, 1)
+template <int BN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmAsRoles<EW>::THREADS, 1)
 gemm2_astat_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmCtail, GemmParams p) {
-    using L = GemmAsSmem<BN>;
+    using L = GemmAsSmem<BN, EW>;
+    constexpr int SUBS = EW / 4;                         // epilogue warps per TMEM lane quarter
     constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     constexpr int STAGES = L::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -609,7 +615,7 @@ gemm2_astat_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
+            mbar_init(&tempty_bar[s], 2 * EW);
         }
         for (int s = 0; s < GEMM_AS_MAX_KB; ++s) {
             mbar_init(&a_full[s], 1);
@@ -674,10 +680,10 @@ gemm2_astat_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 }
             }
         }
-    } else if (warp < GEMM_AS_W_TMA_A) {
-        // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+    } else if (warp < GemmAsRoles<EW>::W_TMA_A) {
+        // ------------------------------------------------------------------ epilogue (warps 2..2+EW-1 of both CTAs)
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int sub = (warp - 2) >> 2;
         uint8_t* slab = smem + L::EPI_OFFSET + (warp - 2) * L::EPI_WARP_BYTES;
         int as = 0, buf = 0, tile_parity = 0;
         uint32_t aphase = 0;
@@ -690,7 +696,7 @@ gemm2_astat_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 tc_fence_after();
                 const int m_warp = m_blk * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32;
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-                epilogue_store_tile<BN, 1>(p, tmC, tmCtail, slab, buf, t_row, m_warp, n_blk, half ^ (tile_parity & 1), lane);
+                epilogue_store_tile<BN, 1, SUBS>(p, tmC, tmCtail, slab, buf, t_row, m_warp, n_blk, (sub + tile_parity) % SUBS, lane);
                 tc_fence_before();
                 __syncwarp();
                 if (elect_one()) mbar_arrive_cluster(as == 0 ? leader_tempty0 : leader_tempty1);
@@ -719,15 +725,15 @@ gemm2_astat_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     if (warp == 1) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
 }
 
-template <int BN>
+template <int BN, int EW>
 static int launch_gemm2_astat(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmCtail,
                               const GemmParams& p, cudaStream_t stream) {
-    using L = GemmAsSmem<BN>;
+    using L = GemmAsSmem<BN, EW>;
     int num_sms = 0;
-    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(gemm2_astat_bf16_tn_kernel<BN>), L::TOTAL));
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(gemm2_astat_bf16_tn_kernel<BN, EW>), L::TOTAL));
     B200X_TRY(device_sm_count(&num_sms));
     const int pairs = std::min(ceil_div(p.M, 2 * GEMM_BM), num_sms / 2);
-    gemm2_astat_bf16_tn_kernel<BN><<<2 * pairs, GEMM_AS_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmCtail, p);
+    gemm2_astat_bf16_tn_kernel<BN, EW><<<2 * pairs, GemmAsRoles<EW>::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmCtail, p);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }
@@ -1070,8 +1076,9 @@ extern "C" int b200x_gemm_bf16(const void* d_a, int lda, const void* d_w, int ld
     B200X_TRY(device_sm_count(&num_sms_d));
     const bool astat = pair && out_mode == B200X_GEMM_OUT_BF16 && (block_n == 192 || block_n == 208) && K % GEMM_BK == 0 &&
                        K <= GEMM_AS_MAX_KB * GEMM_BK && N >= 4 * block_n && ceil_div(M, 2 * GEMM_BM) >= 4 * (num_sms_d / 2);
-    if (astat && block_n == 192) return launch_gemm2_astat<192>(tmA, tmB, tmC, tmCtail, p, s);
-    if (astat && block_n == 208) return launch_gemm2_astat<208>(tmA, tmB, tmC, tmCtail, p, s);
+    if (astat && block_n == 192) return launch_gemm2_astat<192, 8>(tmA, tmB, tmC, tmCtail, p, s);
+    if (astat && block_n == 208) return act_gelu ? launch_gemm2_astat<208, B200X_FC1_EPI_WARPS>(tmA, tmB, tmC, tmCtail, p, s)
+                                                 : launch_gemm2_astat<208, 8>(tmA, tmB, tmC, tmCtail, p, s);
     if (pair) {
         switch (block_n) {
             case 192: return launch_gemm2<192>(tmA, tmB, tmC, tmCtail, p, s);
@@ -1144,8 +1151,9 @@ extern "C" int b200x_gemm_bf16_astationary(const void* d_a, int lda, const void*
     B200X_TRY(make_tmap(&tmC, d_out, 2, 2, dc, sc, bc, 1));
     B200X_TRY(make_tmap(&tmCtail, d_out, 2, 2, dc, sc, bt, 0));
     GemmParams p{M, N, K, d_out, ldc, B200X_GEMM_OUT_BF16, d_bias, act_gelu, nullptr, 0, 0, 0, nullptr, reverse ? 1 : 0};
-    if (block_n == 208) return launch_gemm2_astat<208>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream));
-    return launch_gemm2_astat<192>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream));
+    if (block_n == 208) return act_gelu ? launch_gemm2_astat<208, B200X_FC1_EPI_WARPS>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream))
+                                        : launch_gemm2_astat<208, 8>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream));
+    return launch_gemm2_astat<192, 8>(tmA, tmB, tmC, tmCtail, p, static_cast<cudaStream_t>(stream));
 }
 
 /* Token-mode GEMM whose A operand is M-major: d_img bf16 [batch][K][128] (one 128-row tile per batch element, rows = the
