@@ -565,7 +565,6 @@ def hbm_stages(ctx: Ctx, peaks, copies: int = 64):
     cmax = torch.zeros(copies, n_cta, device="cuda")
     rng = torch.zeros(copies, 2, dtype=torch.int32, device="cuda")
     img_t = torch.zeros(copies, 3744, 128, dtype=torch.bfloat16, device="cuda")
-    img_f = torch.zeros(copies, 128, 3744, dtype=torch.bfloat16, device="cuda")
     part = torch.zeros(copies * 64, dtype=torch.float64, device="cuda")
     fl = torch.zeros(copies, device="cuda")
     null = C.c_void_p(0)
@@ -593,8 +592,8 @@ def hbm_stages(ctx: Ctx, peaks, copies: int = 64):
                                                                 n_frames, P(cmax), null, 0, null), "mel")), copies * (4 * L + 4 * 128 * n_frames))
     k["normalize_resize"] = (run(lambda: ctx.check(lib.b200x_mel_normalize_resize(P(db), n_frames, P(cmax), n_cta, copies, n_frames, 128, 80.0, 1,
                                                                                   1e-6, 3744, null, null, null, null, P(part), P(fl), P(img_t),
-                                                                                  P(img_f), 3744, null), "resize")),
-                             copies * (4 * 128 * n_frames + 2 * 2 * 128 * 3744))
+                                                                                  null, 3744, null), "resize")),
+                             copies * (4 * 128 * n_frames + 2 * 128 * 3744))          # one image: the engine's 128-mel path
     k["istft_masked_sparse"] = (run(lambda: ctx.check(lib.b200x_istft_masked(P(S), 1028, n_frames, copies, 1, P(wins), 0.0, null, P(y), L + 8, null,
                                                                              P(rng), sparse_frames, null), "istft")),
                                 copies * (8 * 1025 * (sparse_frames + 3) + 4 * 512 * (sparse_frames + 3)))
@@ -605,9 +604,20 @@ def hbm_stages(ctx: Ctx, peaks, copies: int = 64):
            "note": "algorithmic bytes per launch (SURVEY 8d) / CUDA-event time; the FFT-based kernels are bound by fp32 issue, not by HBM: "
                    "a 2048-point real FFT is ~65 kFLOP per frame = 25 FLOP per algorithmic byte, i.e. 163 TFLOP/s would be needed at the "
                    "HBM roofline against a 72 TFLOP/s fp32 peak (DESIGN.md 3.3)"}
+    # the bound that applies to the FFT kernels: fp32 issue.  65 kFLOP per 2048-point real frame (5 N log2 N of the 1024-point
+    # complex FFT + real-FFT pre / post pass + window + power / mel or overlap-add) against 148 SMs x 128 lanes x 2 x 1.965 GHz
+    FRAME_FLOP, FP32_PEAK = 65.0e3, 148 * 128 * 2 * 1.965e9 / 1e12
+    frames = {"stft": n_frames, "istft_masked_dense": copies * n_frames, "mel_db_dense": copies * n_frames,
+              "istft_masked_sparse": copies * (sparse_frames + 3), "mel_db_sparse": copies * sparse_frames}
+    out["fp32_peak_tflops"] = FP32_PEAK
     for name, (us, nbytes) in k.items():
         gbs = nbytes / us / 1e3
         out[name] = {"us": us, "algorithmic_bytes": int(nbytes), "gbs": gbs, "frac": gbs / peaks["hbm_gbs"]}
+        if name in frames:
+            tf = frames[name] * FRAME_FLOP / us / 1e6
+            out[name].update(bound="fp32", frames=int(frames[name]), fp32_tflops=tf, fp32_frac=tf / FP32_PEAK)
+        else:
+            out[name]["bound"] = "hbm"
     return out
 
 
