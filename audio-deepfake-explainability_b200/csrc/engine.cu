@@ -222,9 +222,9 @@ int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const dou
     // 229-copy activations are 0.25-1.1 GB per tensor).  The direction is a launch ARGUMENT (no process-wide state).
     int rev = 1;                          // the first LayerNorm walks forward (rev flips to 0 before its launch)
     auto dir = [&]() { if (e->alternate) rev ^= 1; else rev = 0; return rev; };
-    // With the LayerNorm tail (default) fc2 leaves h = LayerNorm_1(x) of the NEXT block behind (b200x_gemm_resid_ln_bf16), so
-    // LN1 is a pass of its own only in the first block.  LN2 stays a separate pass: behind the K = 384 attention projection
-    // the tail measured slower than the two kernels (its re-read of x misses L2; see gemm_tcgen05.cu).
+    // With the LayerNorm tail (default) every residual GEMM leaves h = LayerNorm(x) for the projection that follows it
+    // (b200x_gemm_resid_ln_bf16: proj -> LN2 -> fc1 with the load-add-store epilogue, fc2 -> next block's LN1 -> QKV with the
+    // reduce-add epilogue); only the first block's LN1 is a pass of its own.
     const bool fuse = e->fuse_ln && D % 128 == 0 && D <= 384;
     for (int l = 0; l < c.num_layers; ++l) {
         LayerW& w = e->layers[l];
@@ -237,11 +237,16 @@ int forward_chunk_body(b200x_engine* e, int copies, int64_t n_samples, const dou
         TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.qkv_w.p, D, M, 3 * D, D, pick_block_n(3 * D, D), e->qkv.p, 3 * D, B200X_GEMM_OUT_BF16,
                                   c.qkv_bias ? w.qkv_b.as<float>() : nullptr, 0, nullptr, nullptr, 0, 0, 0, dir(), s));
         TIMED(KC_ATTN, b200x_attention(e->qkv.p, e->att.p, copies, T, c.num_heads, D / c.num_heads, dir(), s));
-        TIMED(KC_GEMM, b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D, D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
-                                  w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, dir(), s));
-        TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
-                                  c.block_ln_eps, e->h.p, nullptr, dir(), s));
-        e->launches += 1;
+        if (fuse) {
+            TIMED(KC_GEMM, b200x_gemm_resid_ln_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, e->x.as<float>(), D, w.proj_b.as<float>(),
+                                               w.n2_g.as<float>(), w.n2_b.as<float>(), c.block_ln_eps, e->h.p, D, dir(), s));
+        } else {
+            TIMED(KC_GEMM, b200x_gemm_bf16(e->att.p, D, w.proj_w.p, D, M, D, D, pick_block_n(D, D), e->x.p, D, B200X_GEMM_OUT_F32_RESID,
+                                      w.proj_b.as<float>(), 0, e->x.as<float>(), nullptr, 0, 0, 0, dir(), s));
+            TIMED(KC_LN, b200x_layernorm(e->x.as<float>(), M, D, w.n2_g.as<float>(), w.n2_b.as<float>(), nullptr, nullptr, 0, 0,
+                                      c.block_ln_eps, e->h.p, nullptr, dir(), s));
+            e->launches += 1;
+        }
         TIMED(KC_GEMM, b200x_gemm_bf16(e->h.p, D, w.fc1_w.p, D, M, e->Hp, D, pick_block_n(e->Hp, D), e->hid.p, e->Hp, B200X_GEMM_OUT_BF16,
                                   w.fc1_b.as<float>(), 1, nullptr, nullptr, 0, 0, 0, dir(), s));
         if (fuse && !last) {

@@ -15,6 +15,7 @@
 // Hence the CTA-pair kernel below (cta_group::2: half of the B tile per SM) for everything but the tokenizer epilogue.
 // Used for every dense contraction of the SpecTTTra forward (tokenizer projections, QKV, attention projection, MLP).
 #include <algorithm>
+#include <type_traits>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -752,9 +753,9 @@ static int launch_gemm2_astat(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 //                  behind the MMAs; ln_done[] stops the epilogue from lapping them.
 // Measured (229 copies, profiles/r02_h_gemm_resid_ln.txt): fc2 + tail 379 us against 310 + 107 us for the two kernels, but
 // proj + tail 322 us against 211 + 107 us: ncu shows the tail's re-read of x coming from DRAM after all (1.17 GB read per call
-// = A + reduce-add RMW + 0.45 GB) - lines produced by TMA reduce-adds are not retained in L2 (an evict_last cache hint on the
-// reduction changes nothing), so the K = 384 projection, already at 5.7 TB/s, only gets longer.  The engine therefore uses
-// the tail behind fc2 (K = 1040, tensor-bound with HBM headroom) and keeps the separate LayerNorm pass behind proj.
+// = A + reduce-add RMW + 0.45 GB) - lines produced by TMA reduce-adds are not served from L2 to later readers (an evict_last
+// hint on the reduction, or prefetching the lines ahead of it, changes nothing).  Behind the K = 384 projection the kernel
+// therefore runs its load-add-store epilogue (LS, below): 303 us, 0.99 GB read.
 constexpr int GEMM_RLN_LN_WARPS = 8;                  // 4 warps: fc2 + tail 469 us, 16 warps (72 registers): 385-417 us, 8: 377 us
                                                       // (profiles/r02_h_gemm_resid_ln.txt, last block)
 // warp roles: the SM's warp arbiter prefers HIGHER warp ids, and a TMA producer / MMA issuer that loses its issue slots to the
@@ -810,11 +811,31 @@ __device__ __forceinline__ void epilogue_resid_tile(const GemmParams& p, const C
     }
 }
 
+// Load-add-store form of the residual epilogue (LS = true): x_old comes in by TMA (32 x 32 fp32 boxes, requested one tile ahead),
+// v = (acc + bias) + x_old is formed in registers - the same sum the reduce-add forms in L2, bit for bit - and goes back by a plain
+// TMA store from the slab it arrived in.  Plain stores leave their lines in L2, so the LayerNorm tail's re-read of the row tile
+// is served from L2; the result of a TMA reduce-add is not (the tail behind the reduce-add epilogue re-read 0.45 GB per call from
+// DRAM).  Three 4 KB slabs per epilogue warp (one per column group of a tile) leave room for a four-stage ring.
+constexpr int GEMM_RLS_SLABS = 3;
 template <int BN>
+struct GemmRlsSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_WARP_BYTES = GEMM_RLS_SLABS * GEMM_SLAB_BYTES;
+    static constexpr int STAGES = (232448 - 1024 - 512 - GEMM_EPI_WARPS * EPI_WARP_BYTES) / STAGE_BYTES;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + GEMM_EPI_WARPS * EPI_WARP_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+    static_assert(BN == 192, "three column groups per epilogue warp and tile");
+    static_assert(STAGES >= 4 && TOTAL <= 232448, "shared memory budget exceeded");
+};
+
+template <int BN, bool LS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_RLN_THREADS, 1)
 gemm2_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, GemmParams p, GemmLnTail q) {
-    using L = Gemm2Smem<BN>;
+    using L = typename std::conditional<LS, GemmRlsSmem<BN>, Gemm2Smem<BN>>::type;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     constexpr int STAGES = L::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -825,7 +846,8 @@ gemm2_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* tempty_bar = tfull_bar + 2;
     uint64_t* x_ready = tempty_bar + 2;                  // [2] this CTA's rows of the row tile are final in L2
     uint64_t* ln_done = x_ready + 2;                     // [2] the LayerNorm warps have consumed x_ready[b]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_done + 2);
+    uint64_t* xfull_bar = ln_done + 2;                   // LS: [8 warps][3] x_old box has landed in the warp's slab
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull_bar + (LS ? GEMM_EPI_WARPS * GEMM_RLS_SLABS : 0));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -849,6 +871,7 @@ gemm2_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             mbar_init(&x_ready[s], GEMM_EPI_WARPS);
             mbar_init(&ln_done[s], GEMM_RLN_LN_WARPS);
         }
+        if (LS) for (int s = 0; s < GEMM_EPI_WARPS * GEMM_RLS_SLABS; ++s) mbar_init(&xfull_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == GEMM_RLN_W_MMA) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
@@ -911,18 +934,82 @@ gemm2_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // ------------------------------------------------------------------ epilogue (warps 8..15 of both CTAs)
         const int quarter = warp & 3;
         const int half = (warp - GEMM_RLN_W_EPI) >> 2;
-        uint8_t* slab = smem + L::EPI_OFFSET + (warp - GEMM_RLN_W_EPI) * GEMM_EPI_WARP_BYTES;
+        uint8_t* slab = smem + L::EPI_OFFSET + (warp - GEMM_RLN_W_EPI) * (LS ? GEMM_RLS_SLABS * GEMM_SLAB_BYTES : GEMM_EPI_WARP_BYTES);
         int as = 0, buf = 0, tile_parity = 0, it = 0;
         uint32_t aphase = 0;
         const uint32_t leader_tempty0 = mapa_shared(&tempty_bar[0], 0), leader_tempty1 = mapa_shared(&tempty_bar[1], 0);
+        // LS: the x_old box of column group li (0..2) of tile `seq` of this warp lives in slab li; seq counts this pair's tiles
+        uint64_t* xfull = xfull_bar + (warp - GEMM_RLN_W_EPI) * GEMM_RLS_SLABS;
+        uint32_t xph = 0;                                // bit li: parity of the next completion of xfull[li]
+        const int my_tiles = (m_tiles - pair + n_pairs - 1) / n_pairs * n_tiles;
+        auto tile_of = [&](int seq, int& m_warp_o, int& n_blk_o, int& half_o) {
+            const int mt_s = pair + (seq / n_tiles) * n_pairs;
+            const int m_blk_s = p.reverse ? m_tiles - 1 - mt_s : mt_s;
+            m_warp_o = m_blk_s * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32;
+            n_blk_o = seq % n_tiles;
+            half_o = half ^ (seq & 1);
+        };
+        auto load_x = [&](int seq, int li) {             // elected lane: request x_old of group li of tile seq (if it exists)
+            int mw, nb, hf;
+            tile_of(seq, mw, nb, hf);
+            const int n0 = nb * BN + (hf + 2 * li) * 32;
+            if (mw >= p.M || n0 >= p.N) return;
+            mbar_expect_tx(&xfull[li], GEMM_SLAB_BYTES);
+            tma_load_2d(slab + li * GEMM_SLAB_BYTES, &tmC, &xfull[li], n0, mw);
+        };
+        if (LS && my_tiles > 0 && elect_one()) {
+#pragma unroll
+            for (int li = 0; li < GEMM_RLS_SLABS; ++li) load_x(0, li);
+        }
+        int seq = 0;
         for (int mt = pair; mt < m_tiles; mt += n_pairs, ++it) {
             const int m_blk = p.reverse ? m_tiles - 1 - mt : mt;
-            for (int n_blk = 0; n_blk < n_tiles; ++n_blk, ++tile_parity) {
+            for (int n_blk = 0; n_blk < n_tiles; ++n_blk, ++tile_parity, ++seq) {
                 mbar_wait(&tfull_bar[as], aphase);
                 tc_fence_after();
                 const int m_warp = m_blk * 2 * GEMM_BM + static_cast<int>(rank) * GEMM_BM + quarter * 32;
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-                epilogue_resid_tile<BN>(p, tmC, slab, buf, t_row, m_warp, n_blk, half ^ (tile_parity & 1), lane);
+                if (LS) {
+                    const int hf = half ^ (seq & 1);
+                    const int sw = lane & 7;
+                    const bool more = seq + 1 < my_tiles;
+#pragma unroll 1
+                    for (int li = 0; li < GEMM_RLS_SLABS; ++li) {
+                        const int c = (hf + 2 * li) * 32;
+                        const int n0 = n_blk * BN + c;
+                        if (m_warp >= p.M || n0 >= p.N) continue;        // no load was requested for it either (load_x)
+                        uint8_t* xs = slab + li * GEMM_SLAB_BYTES;
+                        uint32_t r[32];
+                        tmem_ld32(t_row + c, r);
+                        mbar_wait(&xfull[li], (xph >> li) & 1);
+                        xph ^= 1u << li;
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias != nullptr && n0 + 4 * j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * j));
+                            float4* cell = reinterpret_cast<float4*>(xs + lane * 128 + ((j ^ sw) << 4));
+                            const float4 xo = *cell;
+                            *cell = make_float4((__uint_as_float(r[4 * j]) + b.x) + xo.x, (__uint_as_float(r[4 * j + 1]) + b.y) + xo.y,
+                                                (__uint_as_float(r[4 * j + 2]) + b.z) + xo.z, (__uint_as_float(r[4 * j + 3]) + b.w) + xo.w);
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (elect_one()) {
+                            tma_store_2d(&tmC, xs, n0, m_warp);          // rows >= M are clipped by TMA
+                            bulk_commit();
+                        }
+                    }
+                    // the next tile's x_old boxes, requested a whole tile ahead (independently of what this tile skipped:
+                    // with a ragged last row tile walked first, a warp without rows here still has rows in the next tile)
+                    if (more && elect_one()) {
+                        bulk_wait_read<0>();                             // the slabs' stores have been read out
+#pragma unroll
+                        for (int li = 0; li < GEMM_RLS_SLABS; ++li) load_x(seq + 1, li);
+                    }
+                } else {
+                    epilogue_resid_tile<BN>(p, tmC, slab, buf, t_row, m_warp, n_blk, half ^ (tile_parity & 1), lane);
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (elect_one()) mbar_arrive_cluster(as == 0 ? leader_tempty0 : leader_tempty1);
@@ -980,15 +1067,15 @@ gemm2_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == GEMM_RLN_W_MMA) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
 }
 
-template <int BN>
+template <int BN, bool LS>
 static int launch_gemm2_resid_ln(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                                  const GemmLnTail& q, cudaStream_t stream) {
-    using L = Gemm2Smem<BN>;
+    using L = typename std::conditional<LS, GemmRlsSmem<BN>, Gemm2Smem<BN>>::type;
     int num_sms = 0;
-    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(gemm2_resid_ln_kernel<BN>), L::TOTAL));
+    B200X_TRY(ensure_kernel_smem(reinterpret_cast<const void*>(gemm2_resid_ln_kernel<BN, LS>), L::TOTAL));
     B200X_TRY(device_sm_count(&num_sms));
     const int pairs = std::min(ceil_div(p.M, 2 * GEMM_BM), num_sms / 2);
-    gemm2_resid_ln_kernel<BN><<<2 * pairs, GEMM_RLN_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, p, q);
+    gemm2_resid_ln_kernel<BN, LS><<<2 * pairs, GEMM_RLN_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, p, q);
     B200X_CUDA_TRY(cudaGetLastError());
     return B200X_OK;
 }
@@ -1123,7 +1210,11 @@ extern "C" int b200x_gemm_resid_ln_bf16(const void* d_a, int lda, const void* d_
     B200X_TRY(make_tmap(&tmC, d_x, 4, 2, dc, sc, bc, 1));
     GemmParams p{M, N, K, d_x, ldx, B200X_GEMM_OUT_F32_RESID, d_bias, 0, nullptr, 0, 0, 0, nullptr, reverse ? 1 : 0};
     GemmLnTail q{d_x, ldx, d_gamma, d_beta, eps, reinterpret_cast<__nv_bfloat16*>(d_h), ldh};
-    return launch_gemm2_resid_ln<BN>(tmA, tmB, tmC, p, q, static_cast<cudaStream_t>(stream));
+    // short K (attention projection): the load-add-store epilogue - its plain stores leave about half of the row tile in L2 for
+    // the tail (303 us against 320 us with reduce-adds, 211 + 107 us as two kernels); long K (fc2): the reduce-add epilogue with
+    // its five-stage ring (381 us against 425-449 us; 310 + 107 us as two kernels) - profiles/r02_h_gemm_resid_ln.txt
+    if (K <= 512) return launch_gemm2_resid_ln<BN, true>(tmA, tmB, tmC, p, q, static_cast<cudaStream_t>(stream));
+    return launch_gemm2_resid_ln<BN, false>(tmA, tmB, tmC, p, q, static_cast<cudaStream_t>(stream));
 }
 
 /* The A-stationary kernel on its own (b200x_gemm_bf16 picks it for wide bf16 outputs of a narrow K at large M): bf16 output,
