@@ -941,6 +941,7 @@ gemm2_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // LS: the x_old box of column group li (0..2) of tile `seq` of this warp lives in slab li; seq counts this pair's tiles
         uint64_t* xfull = xfull_bar + (warp - GEMM_RLN_W_EPI) * GEMM_RLS_SLABS;
         uint32_t xph = 0;                                // bit li: parity of the next completion of xfull[li]
+        const uint64_t pol_last = l2_policy_evict_last();   // the tail re-reads these lines within a tile time
         const int my_tiles = (m_tiles - pair + n_pairs - 1) / n_pairs * n_tiles;
         auto tile_of = [&](int seq, int& m_warp_o, int& n_blk_o, int& half_o) {
             const int mt_s = pair + (seq / n_tiles) * n_pairs;
@@ -996,7 +997,7 @@ gemm2_resid_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         fence_proxy_async();
                         __syncwarp();
                         if (elect_one()) {
-                            tma_store_2d(&tmC, xs, n0, m_warp);          // rows >= M are clipped by TMA
+                            tma_store_2d_hint(&tmC, xs, n0, m_warp, pol_last);   // rows >= M are clipped by TMA; evict_last: -2 %
                             bulk_commit();
                         }
                     }
